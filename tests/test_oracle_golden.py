@@ -1,0 +1,249 @@
+"""The CPU restatement (oracle/ideal_oracle.py) against vectors produced by the reference's own source
+(tests/golden/*.npz, see oracle/gen_golden.py).  fp32 restatement: <= 3e-6 of the tensor's max;
+fp64 restatement: <= 1e-5 (it differs from the fp32 reference by the reference's own rounding)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import ideal_oracle as orc
+
+T = torch.from_numpy
+TOL32 = 3e-6
+TOL64 = 1e-5
+DT = [(torch.float32, TOL32), (torch.float64, TOL64)]
+
+
+def tt(a, grad=False, rdtype=torch.float32):
+    t = T(np.ascontiguousarray(a)).to(rdtype)
+    return t.requires_grad_(True) if grad else t
+
+
+def npy(t):
+    return t.detach().numpy()
+
+
+def test_gen_tevar(golden):
+    g = golden("tables")
+    assert_close(npy(orc.gen_TEvar(6, 2, orig=True)), g["te_orig6"], 1e-7)
+    assert_close(npy(orc.gen_TEvar(3, 1, orig=True)), g["te_orig3"], 1e-7)
+    assert_close(npy(orc.gen_TEvar(12, 1, orig=True)), g["te_orig12"], 1e-7)
+    assert_close(npy(orc.gen_TEvar(6, 2, TE_ini_min=0.879e-3, TE_ini_d=None, d_TE_min=0.6623e-3, d_TE_d=None)),
+                 g["te_3T"], 1e-7)
+    np.random.seed(7)
+    assert_close(npy(orc.gen_TEvar(8, 3)), g["te_rand_seed7"], 1e-7)
+    np.random.seed(7)
+    assert_close(npy(orc.gen_TEvar(6, 2, TE_ini_d=0.4e-3, d_TE_min=1.0e-3, d_TE_d=0.3e-3)), g["te_rand_bip_seed7"], 1e-7)
+
+
+@pytest.mark.parametrize("case", ["orig6_1p5", "rand6_3p0", "rand12_1p5", "rand3_1p5"])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_gen_M_and_A(golden, case, rdtype, tol):
+    g = golden("tables")
+    te, field = g[case + "_te"], float(g[case + "_field"])
+    M, Mp, Hp = orc.gen_M(tt(te), field=field, get_H=True, rdtype=rdtype)
+    _, P0, _ = orc.gen_M(tt(te), field=field, get_P0=True, rdtype=rdtype)
+    assert_close(npy(M), g[case + "_M"], tol, "M")
+    assert_close(npy(Mp), g[case + "_Mpinv"], tol, "Mpinv")
+    assert_close(npy(Hp), g[case + "_Hpinv"], tol, "Hpinv")
+    assert_close(npy(P0), g[case + "_P0"], 4 * tol, "P0")
+    A, Ap, AtAp = orc.gen_A(M, gen_AtA_pinv=True)
+    assert_close(npy(A), g[case + "_A"], tol, "A")
+    assert_close(npy(Ap), g[case + "_Apinv"], 4 * tol, "Apinv")
+    if te.shape[1] > 3:          # AtA is numerically singular for ne == 3 with near-uniform TEs
+        assert_close(npy(AtAp), g[case + "_AtApinv"], 2e-3, "AtApinv")
+    assert orc.gen_M(tt(te), get_Mpinv=False, get_P0=True) is None      # reference arity quirk (:70-77)
+
+
+def test_survey_kat_fat_column(golden):
+    """SURVEY.md §8c KAT (v): fat phasor at 1.5 T, orig TEs."""
+    M = npy(orc.gen_M(orc.gen_TEvar(6, 1, orig=True), get_Mpinv=False))[0, :, 1]
+    kat = np.array([-0.0613 - 0.8801j, -0.0659 + 0.8325j, 0.3381 - 0.6391j, -0.3610 + 0.5178j, 0.3625 - 0.4247j,
+                    -0.5197 + 0.3386j])
+    assert np.max(np.abs(M - kat)) < 6e-5
+
+
+def test_eigenvals(golden):
+    g = golden("tables")
+    xy, ratio = orc.eigenvals(tt(g["eig_X"]))
+    assert_close(npy(xy), g["eig_xy"], 1e-6)
+    assert_close(npy(ratio), g["eig_ratio"], 1e-6)
+
+
+FWD = [("wfpm_orig6", "wfpm"), ("wfpm_bip_rand6", "wfpm"), ("wfpm_rand3", "wfpm"), ("wfpm_bip_rand12", "wfpm"),
+       ("ffpd_orig6", "ffpd"), ("ffpd_rand5", "ffpd"), ("magpha_rand6", "magpha"), ("magpha_orig4", "magpha")]
+
+
+@pytest.mark.parametrize("name,model", FWD)
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_forward_models(golden, name, model, rdtype, tol):
+    g = golden("forward")
+    field = float(g[name + "_field"])
+    m = tt(g[name + "_maps"], grad=True, rdtype=rdtype)
+    te = tt(g[name + "_te"])
+    if model == "wfpm":
+        y = orc.IDEAL_Layer(field=field, r2_sc=float(g[name + "_r2sc"]))(m, te=te, rdtype=rdtype)
+    else:
+        y = orc.IDEAL_mag_Layer(field=field, sep_phase=(model == "magpha"))(m, te, rdtype=rdtype)
+    assert_close(npy(y), g[name + "_out"], tol, "signal")
+    (gm,) = torch.autograd.grad((y * tt(g[name + "_up"], rdtype=rdtype)).sum(), [m])
+    assert_close(npy(gm), g[name + "_gmaps"], 2 * tol, "grad maps")
+
+
+def test_forward_default_te(golden):
+    g = golden("forward")
+    y = orc.IDEAL_Layer()(tt(g["wfpm_default_maps"]), ne=4)
+    assert_close(npy(y), g["wfpm_default_out"], TOL32)
+
+
+@pytest.mark.parametrize("name", ["rho_orig6", "rho_rand6_pc", "rho_rand9"])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_get_rho(golden, name, rdtype, tol):
+    g = golden("solve")
+    a, p = tt(g[name + "_acqs"], True, rdtype), tt(g[name + "_pm"], True, rdtype)
+    rho, dem = orc.get_rho(a, p, field=float(g[name + "_field"]), te=tt(g[name + "_te"]), r2_sc=float(g[name + "_r2sc"]),
+                           phase_constraint=bool(g[name + "_pc"]), acq_demod=True, rdtype=rdtype)
+    assert_close(npy(rho), g[name + "_rho"], tol, "rho")
+    assert_close(npy(dem), g[name + "_demod"], tol, "demod")
+    loss = (rho * tt(g[name + "_up_rho"], rdtype=rdtype)).sum() + (dem * tt(g[name + "_up_demod"], rdtype=rdtype)).sum()
+    ga, gp = torch.autograd.grad(loss, [a, p])
+    gtol = 2e-4 if bool(g[name + "_pc"]) else 2 * tol       # angle() near the branch cut amplifies rounding
+    assert_close(npy(ga), g[name + "_gacqs"], gtol, "grad acqs")
+    assert_close(npy(gp), g[name + "_gpm"], gtol, "grad pm")
+
+
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_get_rho_bipolar_and_flat(golden, rdtype, tol):
+    g = golden("solve")
+    a, p = tt(g["rho_bip_acqs"], True, rdtype), tt(g["rho_bip_pm"], True, rdtype)
+    rho = orc.get_rho(a, p, te=tt(g["rho_bip_te"]), rdtype=rdtype)
+    assert_close(npy(rho), g["rho_bip_rho"], tol)
+    ga, gp = torch.autograd.grad((rho * tt(g["rho_bip_up_rho"], rdtype=rdtype)).sum(), [a, p])
+    assert_close(npy(ga), g["rho_bip_gacqs"], 2 * tol)
+    assert_close(npy(gp), g["rho_bip_gpm"], 2 * tol)
+    a, p = tt(g["rho_flat_acqs"], True, rdtype), tt(g["rho_flat_pm"], True, rdtype)
+    rho = orc.get_rho(a, p, MEBCRN=False, rdtype=rdtype)
+    assert_close(npy(rho), g["rho_flat_rho"], tol)
+    ga, gp = torch.autograd.grad((rho * tt(g["rho_flat_up_rho"], rdtype=rdtype)).sum(), [a, p])
+    assert_close(npy(ga), g["rho_flat_gacqs"], 2 * tol)
+    assert_close(npy(gp), g["rho_flat_gpm"], 2 * tol)
+
+
+@pytest.mark.parametrize("name,explicit_te", [("a2a_orig6", False), ("a2a_3T", False), ("a2a_rand7", True)])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_acq_to_acq_and_config2_loss(golden, name, explicit_te, rdtype, tol):
+    g = golden("solve")
+    field = float(g[name + "_field"])
+    te = tt(g[name + "_te"]) if explicit_te else None
+    a, p = tt(g[name + "_acqs"], True, rdtype), tt(g[name + "_pm"], True, rdtype)
+    y = orc.acq_to_acq(a, p, te=te, field=field, legacy_single=True, rdtype=rdtype)
+    assert_close(npy(y), g[name + "_out"], tol, "S_hat")
+    ga, gp = torch.autograd.grad((y * tt(g[name + "_up"], rdtype=rdtype)).sum(), [a, p])
+    assert_close(npy(ga), g[name + "_gacqs"], 2 * tol, "grad acqs")
+    assert_close(npy(gp), g[name + "_gpm"], 2 * tol, "grad pm")
+    # 2-tuple form: second result identical, first equals get_rho
+    rho, y2 = orc.acq_to_acq(a, p, te=te, field=field, rdtype=rdtype)
+    assert_close(npy(y2), g[name + "_out"], tol)
+    assert_close(npy(rho), npy(orc.get_rho(a, p, field=field, te=tt(g[name + "_te"]), rdtype=rdtype)), tol)
+    # config-2 objective
+    p2 = tt(g[name + "_pm"], True, rdtype)
+    loss, _, _ = orc.physics_loss_a2a(tt(g[name + "_acqs"], rdtype=rdtype), p2, te=te, field=field, rdtype=rdtype)
+    assert abs(loss.item() - float(g[name + "_loss"])) <= 1e-5 * float(g[name + "_loss"])
+    (gl,) = torch.autograd.grad(loss, [p2])
+    assert_close(npy(gl), g[name + "_loss_gpm"], 4 * tol, "loss grad pm")
+
+
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_forward_losses(golden, rdtype, tol):
+    g = golden("losses")
+    m = tt(g["c4_maps"], True, rdtype)
+    loss, _ = orc.physics_loss_fwd(tt(g["c4_acqs"], rdtype=rdtype), m, tt(g["c4_te"]), model="magpha", rdtype=rdtype)
+    assert abs(loss.item() - float(g["c4_loss"])) <= 1e-5 * float(g["c4_loss"])
+    (gm,) = torch.autograd.grad(loss, [m])
+    assert_close(npy(gm), g["c4_gmaps"], 4 * tol)
+    m = tt(g["wl_maps"], True, rdtype)
+    loss, _ = orc.physics_loss_fwd(tt(g["wl_acqs"], rdtype=rdtype), m, tt(g["wl_te"]), field=3.0, model="wfpm", rdtype=rdtype)
+    assert abs(loss.item() - float(g["wl_loss"])) <= 1e-5 * float(g["wl_loss"])
+    (gm,) = torch.autograd.grad(loss, [m])
+    assert_close(npy(gm), g["wl_gmaps"], 4 * tol)
+
+
+def test_uq_losses(golden):
+    g = golden("losses")
+    pv = tt(g["vm_predvar"], True)
+    loss = orc.var_mse(tt(g["vm_true"]), pv)
+    assert abs(loss.item() - float(g["vm_loss"])) <= 2e-6 * abs(float(g["vm_loss"]))
+    assert_close(npy(torch.autograd.grad(loss, [pv])[0]), g["vm_grad"], 1e-5)
+    pv = tt(g["vr_predvar"], True)
+    loss = orc.var_mse_r2(tt(g["vr_true"]), pv)
+    assert abs(loss.item() - float(g["vr_loss"])) <= 2e-6 * abs(float(g["vr_loss"]))
+    # d/dz log(i0e(z)) at z ~ 1e5 (variance floor 1e-5) is a difference of near-equal fp32 numbers
+    assert_close(npy(torch.autograd.grad(loss, [pv])[0]), g["vr_grad"], 1e-4)
+
+
+@pytest.mark.parametrize("name", ["cse_1p5", "cse_3p0"])
+def test_cse_mag(golden, name):
+    g = golden("tier2")
+    a, r = tt(g[name + "_mag"], True), tt(g[name + "_r2"], True)
+    params = [float(g[name + "_field"]), tt(g[name + "_te"])]
+    r2sc = float(g[name + "_r2sc"])
+    rho, fit, demod, ls = orc.CSE_mag(a, r, params, r2_sc=r2sc, demod_signal=True)
+    _, _, unc, _ = orc.CSE_mag(a, r, params, r2_sc=r2sc, uncertainty=True)
+    for k, v in [("rho", rho), ("fit", fit), ("demod", demod), ("ls", ls)]:
+        assert_close(npy(v), g[f"{name}_{k}"], 2e-5, k)           # A_pinv by QR in fp32: cond(A) ~ 10-30
+    assert_close(npy(unc), g[name + "_unc"], 5e-3, "unc")         # lambda_min / lambda_max: cancellation
+    assert len(orc.CSE_mag(a, r, params, r2_sc=r2sc)) == 2
+
+
+@pytest.mark.parametrize("name", ["unc_1p5", "unc_3p0_rem"])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_acq_uncertainty(golden, name, rdtype, tol):
+    g = golden("tier2")
+    pv, rm, rv = (tt(g[name + k], True, rdtype) for k in ("_phi_v", "_r2_m", "_r2_v"))
+    kw = dict(ne=6, te=tt(g[name + "_te"]), field=float(g[name + "_field"]), rem_R2=bool(g[name + "_rem"]), rdtype=rdtype)
+    phi = orc.Moments(tt(g[name + "_phi_m"], rdtype=rdtype), pv)
+    r2 = orc.Moments(rm, rv)
+    var = orc.acq_uncertainty(tt(g[name + "_rho"], rdtype=rdtype), phi, r2, **kw)
+    assert_close(npy(var), g[name + "_var"], 4 * tol)
+    var1 = orc.acq_uncertainty(tt(g[name + "_rho"], rdtype=rdtype), phi, r2, only_mag=True, **kw)
+    assert_close(npy(var1), g[name + "_var_mag"], 4 * tol)
+    grads = torch.autograd.grad((var * tt(g[name + "_up"], rdtype=rdtype)).sum(), [pv, rm, rv], allow_unused=True)
+    for gr, k in zip(grads, ("_g_phi_v", "_g_r2_m", "_g_r2_v")):
+        ref = g[name + k]
+        if gr is None:
+            assert not ref.any()
+        else:
+            assert_close(npy(gr), ref, 8 * tol, k)
+
+
+@pytest.mark.parametrize("name", ["pdffu", "pdffu_rem"])
+def test_pdff_uncertainty(golden, name):
+    g = golden("tier2")
+    rho, rvar = orc.PDFF_uncertainty(tt(g[name + "_acqs"]), orc.Moments(tt(g[name + "_phi_m"]), tt(g[name + "_phi_v"])),
+                                     orc.Moments(tt(g[name + "_r2_m"]), tt(g[name + "_r2_v"])), te=tt(g[name + "_te"]),
+                                     rem_R2=bool(g[name + "_rem"]))
+    assert_close(npy(rho), g[name + "_rho"], 2e-5)
+    assert_close(npy(rvar), g[name + "_rho_var"], 2e-5)
+
+
+def test_round_trip_and_idempotence():
+    """SURVEY §8c KATs (i)-(iv) in fp64."""
+    from idealgan import synth
+    rng = np.random.default_rng(5)
+    maps = synth.wfpm_maps(2, 10, 10, rng, neg_r2_frac=0.0, masked=False)
+    te = T(synth.te_random(2, 6, rng))
+    d = torch.float64
+    S = orc.IDEAL_model(T(maps), [1.5, te], rdtype=d)
+    rho = orc.get_rho(S, T(maps[:, 2:3]), te=te, rdtype=d)
+    assert_close(npy(rho), maps[:, :2].astype(np.float64), 1e-12)
+    _, S2 = orc.acq_to_acq(S, T(maps[:, 2:3]), te=te, rdtype=d)
+    assert_close(npy(S2), npy(S), 1e-12)
+    noisy = S + 0.05 * torch.randn_like(S)
+    _, P1 = orc.acq_to_acq(noisy, T(maps[:, 2:3]), te=te, rdtype=d)
+    _, P2 = orc.acq_to_acq(P1, T(maps[:, 2:3]), te=te, rdtype=d)
+    assert_close(npy(P2), npy(P1), 1e-12)
+    pure = np.zeros((1, 3, 4, 4, 2), np.float32)
+    pure[:, 0, :, :, 0] = 0.5
+    S = orc.IDEAL_model(T(pure), [1.5, orc.gen_TEvar(6, 1, orig=True)], rdtype=d)
+    assert_close(npy(S[..., 0]), np.full((1, 6, 4, 4), 0.7), 1e-7)     # rho_sc rounded to fp32 in the input path
+    assert np.abs(npy(S[..., 1])).max() < 1e-12
