@@ -1,0 +1,283 @@
+// Shared device/host helpers for libidealgan (sm_100a only).
+//
+// Design: every kernel is "one thread = two neighbouring voxels", with the two voxels
+// packed in the lanes of Blackwell's f32x2 arithmetic (FFMA2/FMUL2/FADD2 via __ffma2_rn & co., new on
+// sm_100), so the per-voxel complex algebra issues half the FP32 instructions of a scalar kernel while
+// global loads/stores are 16-byte float4 and fully coalesced.  Per-sample constants (echo times, fat
+// phasor, pseudo-inverse rows) are staged once per block in shared memory and enter the packed math as
+// scalar-broadcast operands.  Transcendentals go to the SFU (MUFU.SIN/COS/EX2) after an exact range
+// reduction in turns.  A scalar (one voxel per thread) instantiation of the same templates handles odd
+// voxel counts / unaligned planes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <initializer_list>
+#include <type_traits>
+
+#include "../../include/idealgan.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libidealgan targets sm_100a (B200) only"
+#endif
+
+namespace ig {
+
+constexpr float kFmSc = 300.0f;     // IDEAL_model.py:18
+constexpr float kRhoSc = 1.4f;      // IDEAL_model.py:19
+constexpr float kTwoPi = 6.283185307179586f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+#define IG_CUDA(call)                                                  \
+    do {                                                               \
+        cudaError_t e__ = (call);                                      \
+        if (e__ != cudaSuccess) return ::ig::cuda_fail(e__, #call);    \
+    } while (0)
+#define IG_REQUIRE(cond, code, ...)          \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::ig::set_error(__VA_ARGS__);    \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// lane types: float (one voxel per thread) or pk (two voxels per thread, f32x2 packed)
+// ------------------------------------------------------------------------------------------------
+struct pk {
+    float2 d;
+};
+__device__ __forceinline__ pk mk(float a, float b) { pk r; r.d = make_float2(a, b); return r; }
+
+template <typename V> struct lanes;
+template <> struct lanes<float> { static constexpr int n = 1; };
+template <> struct lanes<pk> { static constexpr int n = 2; };
+
+__device__ __forceinline__ float bc(float s, float) { return s; }          // broadcast scalar to lane type
+__device__ __forceinline__ pk bc(float s, pk) { return mk(s, s); }
+template <typename V> __device__ __forceinline__ V splat(float s) { return bc(s, V{}); }
+
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+
+__device__ __forceinline__ pk vfma(pk a, pk b, pk c) { pk r; r.d = __ffma2_rn(a.d, b.d, c.d); return r; }
+__device__ __forceinline__ pk vmul(pk a, pk b) { pk r; r.d = __fmul2_rn(a.d, b.d); return r; }
+__device__ __forceinline__ pk vadd(pk a, pk b) { pk r; r.d = __fadd2_rn(a.d, b.d); return r; }
+__device__ __forceinline__ pk vneg(pk a) { return mk(-a.d.x, -a.d.y); }
+__device__ __forceinline__ pk vsub(pk a, pk b) { return vfma(mk(-1.0f, -1.0f), b, a); }
+// scalar (block-uniform table coefficient) x packed: the compiler folds make_float2(s, s) into FFMA2's
+// scalar-broadcast operand form (R.F32), so no register pair is materialised.
+__device__ __forceinline__ pk vfma(float a, pk b, pk c) { return vfma(mk(a, a), b, c); }
+__device__ __forceinline__ pk vmul(float a, pk b) { return vmul(mk(a, a), b); }
+
+template <typename V> struct cx {
+    V re, im;
+};
+template <typename V> __device__ __forceinline__ cx<V> czero() { return cx<V>{splat<V>(0.f), splat<V>(0.f)}; }
+// acc += (ar + i ai) * z        (table coefficient times per-voxel complex)
+template <typename V> __device__ __forceinline__ void cmac(cx<V> &acc, float ar, float ai, const cx<V> &z) {
+    acc.re = vfma(ar, z.re, acc.re);
+    acc.re = vfma(-ai, z.im, acc.re);
+    acc.im = vfma(ar, z.im, acc.im);
+    acc.im = vfma(ai, z.re, acc.im);
+}
+// a + (cr + i ci) * b
+template <typename V> __device__ __forceinline__ cx<V> caffine(const cx<V> &a, float cr, float ci, const cx<V> &b) {
+    cx<V> r = a;
+    cmac(r, cr, ci, b);
+    return r;
+}
+template <typename V> __device__ __forceinline__ cx<V> cmulv(const cx<V> &a, const cx<V> &b) {
+    cx<V> r;
+    r.re = vfma(vneg(a.im), b.im, vmul(a.re, b.re));
+    r.im = vfma(a.im, b.re, vmul(a.re, b.im));
+    return r;
+}
+// conj(a) * b
+template <typename V> __device__ __forceinline__ cx<V> cmulc(const cx<V> &a, const cx<V> &b) {
+    cx<V> r;
+    r.re = vfma(a.im, b.im, vmul(a.re, b.re));
+    r.im = vfma(vneg(a.im), b.re, vmul(a.re, b.im));
+    return r;
+}
+template <typename V> __device__ __forceinline__ cx<V> cscale(V s, const cx<V> &a) {
+    return cx<V>{vmul(s, a.re), vmul(s, a.im)};
+}
+
+// ------------------------------------------------------------------------------------------------
+// SFU transcendentals.  Phases are carried in TURNS: tau -> tau - rint(tau) is exact in fp32, after
+// which MUFU.SIN/COS see |x| <= pi where their absolute error is ~2^-21.4.  Decay uses MUFU.EX2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float round_turns(float t) {
+    // round-to-nearest-integer by the 1.5 * 2^23 trick: two FADDs on the FMA pipe, no conversion pipe
+    const float magic = 12582912.0f;
+    float n = __fadd_rn(t, magic);
+    n = __fsub_rn(n, magic);
+    return __fsub_rn(t, n);
+}
+__device__ __forceinline__ void unit_phasor(float turns, float &c, float &s) {
+    float r = round_turns(turns) * kTwoPi;
+    c = __cosf(r);
+    s = __sinf(r);
+}
+__device__ __forceinline__ void unit_phasor(pk turns, pk &c, pk &s) {
+    unit_phasor(turns.d.x, c.d.x, s.d.x);
+    unit_phasor(turns.d.y, c.d.y, s.d.y);
+}
+__device__ __forceinline__ pk fast_ex2(pk x) { return mk(fast_ex2(x.d.x), fast_ex2(x.d.y)); }
+__device__ __forceinline__ float vrelu(float x) { return fmaxf(x, 0.f); }
+__device__ __forceinline__ pk vrelu(pk x) { return mk(fmaxf(x.d.x, 0.f), fmaxf(x.d.y, 0.f)); }
+__device__ __forceinline__ float vgate(float x, float g) { return x > 0.f ? g : 0.f; }      // relu'(x) * g
+__device__ __forceinline__ pk vgate(pk x, pk g) { return mk(x.d.x > 0.f ? g.d.x : 0.f, x.d.y > 0.f ? g.d.y : 0.f); }
+__device__ __forceinline__ float vsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ pk vsqrt(pk x) { return mk(sqrtf(x.d.x), sqrtf(x.d.y)); }
+// (a != 0) ? s - a : 0, per lane -- the reference's where(A != 0, S_hat, 0) followed by (S_hat - A)
+__device__ __forceinline__ float mask_sub(float s, float a) { return a != 0.f ? s - a : 0.f; }
+__device__ __forceinline__ pk mask_sub(pk s, pk a) { return mk(mask_sub(s.d.x, a.d.x), mask_sub(s.d.y, a.d.y)); }
+__device__ __forceinline__ float hsum(float x) { return x; }
+__device__ __forceinline__ float hsum(pk x) { return x.d.x + x.d.y; }
+
+// ------------------------------------------------------------------------------------------------
+// streaming global access.  A complex plane stores (re, im) per voxel; a thread owns lanes<V>::n
+// consecutive voxels starting at voxel index v0 (even for pk), i.e. one 8- or 16-byte access.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cx<float> ld_cx(const float *plane, int v0, float) {
+    float2 t = __ldcs(reinterpret_cast<const float2 *>(plane) + v0);
+    return cx<float>{t.x, t.y};
+}
+__device__ __forceinline__ cx<pk> ld_cx(const float *plane, int v0, pk) {
+    float4 t = __ldcs(reinterpret_cast<const float4 *>(plane) + (v0 >> 1));
+    return cx<pk>{mk(t.x, t.z), mk(t.y, t.w)};
+}
+__device__ __forceinline__ void st_cx(float *plane, int v0, const cx<float> &z) {
+    __stcs(reinterpret_cast<float2 *>(plane) + v0, make_float2(z.re, z.im));
+}
+__device__ __forceinline__ void st_cx(float *plane, int v0, const cx<pk> &z) {
+    __stcs(reinterpret_cast<float4 *>(plane) + (v0 >> 1), make_float4(z.re.d.x, z.im.d.x, z.re.d.y, z.im.d.y));
+}
+// one real value per voxel (plane of nv floats)
+__device__ __forceinline__ void st_real(float *plane, int v0, float x) { __stcs(plane + v0, x); }
+__device__ __forceinline__ void st_real(float *plane, int v0, pk x) {
+    __stcs(reinterpret_cast<float2 *>(plane) + (v0 >> 1), x.d);
+}
+__device__ __forceinline__ float ld_real(const float *plane, int v0, float) { return __ldcs(plane + v0); }
+__device__ __forceinline__ pk ld_real(const float *plane, int v0, pk) {
+    pk r; r.d = __ldcs(reinterpret_cast<const float2 *>(plane) + (v0 >> 1)); return r;
+}
+// lane-wise access helpers for the few strided layouts (flat, mag/phase rows)
+__device__ __forceinline__ float lane_get(float x, int) { return x; }
+__device__ __forceinline__ float lane_get(pk x, int l) { return l ? x.d.y : x.d.x; }
+__device__ __forceinline__ void lane_set(float &x, int, float v) { x = v; }
+__device__ __forceinline__ void lane_set(pk &x, int l, float v) { if (l) x.d.y = v; else x.d.x = v; }
+
+// ------------------------------------------------------------------------------------------------
+// per-sample table staged in shared memory
+// ------------------------------------------------------------------------------------------------
+template <int NE> struct SampleTab {
+    float te[NE];     // seconds
+    float kphi[NE];   // te * fm_sc            : turns per unit of the phi/300 map
+    float kdec[NE];   // -te * r2_sc * log2(e) : log2 of the decay per unit of the R2*/r2_sc map
+    float sgn[NE];    // (-1)^e, e = 1..ne     : bipolar odd/even sign
+    float c_re[NE], c_im[NE];
+    float pw_re[NE], pw_im[NE], pf_re[NE], pf_im[NE];
+    float ap0[NE], ap1[NE], ap2[NE];
+};
+
+template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, const float *__restrict__ tab_b, int ne, float r2_sc) {
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        const bool live = e < ne;
+        const float te = live ? tab_b[IG_ROW_TE * IG_MAX_NE + e] : 0.f;
+        t.te[e] = te;
+        t.kphi[e] = te * kFmSc;
+        t.kdec[e] = -te * r2_sc * kLog2e;
+        t.sgn[e] = (e & 1) ? 1.f : -1.f;
+        t.c_re[e] = live ? tab_b[IG_ROW_C_RE * IG_MAX_NE + e] : 0.f;
+        t.c_im[e] = live ? tab_b[IG_ROW_C_IM * IG_MAX_NE + e] : 0.f;
+        t.pw_re[e] = live ? tab_b[IG_ROW_PW_RE * IG_MAX_NE + e] : 0.f;
+        t.pw_im[e] = live ? tab_b[IG_ROW_PW_IM * IG_MAX_NE + e] : 0.f;
+        t.pf_re[e] = live ? tab_b[IG_ROW_PF_RE * IG_MAX_NE + e] : 0.f;
+        t.pf_im[e] = live ? tab_b[IG_ROW_PF_IM * IG_MAX_NE + e] : 0.f;
+        t.ap0[e] = live ? tab_b[IG_ROW_AP0 * IG_MAX_NE + e] : 0.f;
+        t.ap1[e] = live ? tab_b[IG_ROW_AP1 * IG_MAX_NE + e] : 0.f;
+        t.ap2[e] = live ? tab_b[IG_ROW_AP2 * IG_MAX_NE + e] : 0.f;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss reduction: per-thread partial -> warp shuffle -> block -> one float per block in scratch; the
+// last block to finish (ticket counter) adds the per-block partials in a fixed order in fp64 and
+// writes the scalar, then re-zeroes the ticket so the scratch can be reused by the next launch.
+// scratch layout: [0] unsigned ticket, [16..] float partials[gridDim.x * gridDim.y]
+// ------------------------------------------------------------------------------------------------
+constexpr size_t kScratchHeader = 16;
+
+__device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float *loss_out, float scale) {
+    __shared__ float warp_part[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    unsigned *ticket = reinterpret_cast<unsigned *>(scratch);
+    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + kScratchHeader);
+    const unsigned nblocks = gridDim.x * gridDim.y;
+    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += warp_part[w];
+        partials[bid] = s;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned i = threadIdx.x; i < nblocks; i += blockDim.x) acc += static_cast<double>(__ldcg(partials + i));
+    __shared__ double dpart[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) dpart[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += dpart[w];
+        loss_out[0] = static_cast<float>(s * static_cast<double>(scale));
+        *ticket = 0u;
+    }
+}
+
+// NE buckets: kernels are instantiated for these echo counts; a call with `ne` echoes runs in the
+// smallest bucket >= ne with the unused echoes predicated off (their table entries are zero).
+template <typename F> inline int dispatch_ne(int ne, F &&f) {
+    if (ne <= 4) return f(std::integral_constant<int, 4>{});
+    if (ne <= 6) return f(std::integral_constant<int, 6>{});
+    if (ne <= 8) return f(std::integral_constant<int, 8>{});
+    if (ne <= 12) return f(std::integral_constant<int, 12>{});
+    return f(std::integral_constant<int, 16>{});
+}
+
+inline dim3 grid_for(int nb, int nv, int vpt) {
+    const int per_block = kThreads * vpt;
+    return dim3(static_cast<unsigned>((nv + per_block - 1) / per_block), static_cast<unsigned>(nb), 1);
+}
+
+}  // namespace ig

@@ -1,0 +1,295 @@
+// Forward signal models, their adjoint, and the fused forward -> mask -> MSE -> backward objective.
+//
+// Replaces IDEAL_model / IDEAL_mag / IDEAL_mag_phase of the reference
+// (/root/reference/wflib/IDEAL_model.py:220-299, 404-453, 456-509) and the TF autodiff through them
+// (train-IDEAL-single.py:154-157,175; train-IDEAL-GAN.py:243,288).  The reference materialises
+// ~6 complex (nb, ne, nv) intermediates per call; here each voxel is read once, kept in registers for
+// all echoes, and written once:
+//     S_e = exp(-te_e R) exp(i (2 pi te_e phi + s_e beta)) (rho_W + c_e rho_F),   s_e = (-1)^e
+// Algorithmic HBM bytes per voxel (ne = 6): forward 24|32 read + 48 written; backward 48 + 24|32 read
+// + 24|32 written; fused loss 48 + 24|32 read + 24|32 written.
+#include "ig_common.cuh"
+
+namespace ig {
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_LOSS = 2 };
+
+struct FwdParams {
+    const float *maps;
+    const float *tab;
+    const float *gout;   // MODE_BWD: upstream (nb, ne, nv, 2)
+    const float *acqs;   // MODE_LOSS: measured echoes (nb, ne, nv, 2)
+    float *out;          // MODE_FWD: S_hat ; MODE_LOSS: optional S_hat
+    float *gmaps;
+    float *loss;
+    void *scratch;
+    int rows_or_ch, nb, ne, nv, flags;
+    float r2_sc, inv_n;
+};
+
+// decoded per-voxel model state
+template <typename V> struct Voxel {
+    cx<V> rhoW, rhoF;   // already multiplied by rho_sc
+    V phi_t;            // phi / fm_sc map value
+    V r2raw, r2;        // R2* map value before / after the relu gate
+    V bturn;            // bipolar phase in turns
+    // model-specific leftovers needed by the adjoint
+    cx<V> uW, uF;       // unit phasors of the species phases (FFPD: uW = common phasor)
+    V ff, pd;           // FFPD
+};
+
+template <typename V> __device__ __forceinline__ cx<V> ld_row(const float *maps_b, int row, int nv, int v0) {
+    return ld_cx(maps_b + static_cast<size_t>(row) * nv * 2, v0, V{});
+}
+template <typename V> __device__ __forceinline__ void st_row(float *g_b, int row, int nv, int v0, const cx<V> &z) {
+    st_cx(g_b + static_cast<size_t>(row) * nv * 2, v0, z);
+}
+
+template <typename V, int MODEL> __device__ __forceinline__ Voxel<V> decode(const float *maps_b, int rows_or_ch, int nv, int v0, int flags) {
+    Voxel<V> x;
+    const V zero = splat<V>(0.f);
+    x.bturn = zero;
+    x.ff = zero;
+    x.pd = zero;
+    x.uW = cx<V>{zero, zero};
+    x.uF = cx<V>{zero, zero};
+    if constexpr (MODEL == IG_MODEL_WFPM) {
+        const cx<V> m0 = ld_row<V>(maps_b, 0, nv, v0), m1 = ld_row<V>(maps_b, 1, nv, v0), m2 = ld_row<V>(maps_b, 2, nv, v0);
+        x.rhoW = cx<V>{vmul(kRhoSc, m0.re), vmul(kRhoSc, m0.im)};
+        x.rhoF = cx<V>{vmul(kRhoSc, m1.re), vmul(kRhoSc, m1.im)};
+        x.phi_t = m2.re;
+        x.r2raw = m2.im;
+        x.r2 = (flags & IG_F_NO_RELU) ? m2.im : vrelu(m2.im);
+        if (rows_or_ch > 3) x.bturn = vmul(0.5f, ld_row<V>(maps_b, rows_or_ch - 1, nv, v0).re);   // pi * b / (2 pi)
+    } else if constexpr (MODEL == IG_MODEL_FFPD) {
+        const cx<V> m0 = ld_row<V>(maps_b, 0, nv, v0), m1 = ld_row<V>(maps_b, 1, nv, v0), m2 = ld_row<V>(maps_b, 2, nv, v0);
+        x.ff = m0.re;
+        x.pd = m1.re;
+        x.r2raw = x.r2 = m1.im;
+        x.phi_t = m2.im;
+        unit_phasor(vmul(2.0f, m2.re), x.uW.re, x.uW.im);                                        // 4 pi p / (2 pi)
+        const V a = vmul(kRhoSc, x.pd);
+        const V aw = vfma(vneg(a), x.ff, a), af = vmul(a, x.ff);
+        x.rhoW = cscale(aw, x.uW);
+        x.rhoF = cscale(af, x.uW);
+    } else {
+        V magW, magF, pW, pF;
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            const float *r0 = maps_b + (static_cast<size_t>(v0) + l) * rows_or_ch;
+            const float *r1 = r0 + static_cast<size_t>(nv) * rows_or_ch;
+            float a0, a1, a2, b0, b1, b2, b3 = 0.f;
+            if (rows_or_ch == 4) {
+                const float4 p = __ldcs(reinterpret_cast<const float4 *>(r0)), q = __ldcs(reinterpret_cast<const float4 *>(r1));
+                a0 = p.x; a1 = p.y; a2 = p.z; b0 = q.x; b1 = q.y; b2 = q.z; b3 = q.w;
+            } else {
+                a0 = __ldcs(r0); a1 = __ldcs(r0 + 1); a2 = __ldcs(r0 + 2);
+                b0 = __ldcs(r1); b1 = __ldcs(r1 + 1); b2 = __ldcs(r1 + 2);
+            }
+            lane_set(magW, l, a0); lane_set(magF, l, a1); lane_set(x.r2, l, a2);
+            lane_set(pW, l, b0); lane_set(pF, l, b1); lane_set(x.phi_t, l, b2); lane_set(x.bturn, l, 2.0f * b3);
+        }
+        x.r2raw = x.r2;
+        unit_phasor(vmul(2.0f, pW), x.uW.re, x.uW.im);
+        unit_phasor(vmul(2.0f, pF), x.uF.re, x.uF.im);
+        x.rhoW = cscale(vmul(kRhoSc, magW), x.uW);
+        x.rhoF = cscale(vmul(kRhoSc, magF), x.uF);
+    }
+    return x;
+}
+
+// adjoint accumulators over echoes, all in the demodulated frame (g_e = conj(w_e) G_e, q_e = conj(g_e) yhat_e)
+template <typename V> struct Adj {
+    cx<V> sg;    // sum_e g_e                    = conj(a_W)
+    cx<V> sgc;   // sum_e conj(c_e) g_e          = conj(a_F)
+    cx<V> tq;    // sum_e te_e q_e
+    cx<V> q;     // sum_e q_e
+    V bq;        // sum_e s_e Im q_e
+};
+
+template <typename V, int MODEL>
+__device__ __forceinline__ void write_grads(float *g_b, int rows_or_ch, int nv, int v0, int flags, const Voxel<V> &x, const Adj<V> &a,
+                                            float r2_sc, float scale) {
+    // d/d(phi map) = fm_sc sum_e Re(conj(G) 2 pi i te S) = -2 pi fm_sc Im(tq);  d/d(R2 map) = -r2_sc Re(tq)
+    const V gphi = vmul(-kTwoPi * kFmSc * scale, a.tq.im);
+    V gr2 = vmul(-r2_sc * scale, a.tq.re);
+    const V zero = splat<V>(0.f);
+    if constexpr (MODEL == IG_MODEL_WFPM) {
+        if (!(flags & IG_F_NO_RELU)) gr2 = vgate(x.r2raw, gr2);
+        st_row<V>(g_b, 0, nv, v0, cx<V>{vmul(kRhoSc * scale, a.sg.re), vmul(kRhoSc * scale, a.sg.im)});
+        st_row<V>(g_b, 1, nv, v0, cx<V>{vmul(kRhoSc * scale, a.sgc.re), vmul(kRhoSc * scale, a.sgc.im)});
+        st_row<V>(g_b, 2, nv, v0, cx<V>{gphi, gr2});
+        if (rows_or_ch > 3) st_row<V>(g_b, rows_or_ch - 1, nv, v0, cx<V>{vmul(-0.5f * kTwoPi * scale, a.bq), zero});
+    } else if constexpr (MODEL == IG_MODEL_FFPD) {
+        // Re(u0 conj(z)) = u.re z.re + u.im z.im with z = sg / sgc
+        const V uw = vfma(x.uW.im, a.sg.im, vmul(x.uW.re, a.sg.re));
+        const V uf = vfma(x.uW.im, a.sgc.im, vmul(x.uW.re, a.sgc.re));
+        const V dff = vmul(vmul(kRhoSc * scale, x.pd), vsub(uf, uw));
+        const V mix = vfma(x.ff, vsub(uf, uw), uw);                                   // (1 - ff) uw + ff uf
+        const V dpd = vmul(kRhoSc * scale, mix);
+        const V dpha = vmul(-2.0f * kTwoPi * scale, a.q.im);                          // 4 pi Re(i T)
+        st_row<V>(g_b, 0, nv, v0, cx<V>{dff, zero});
+        st_row<V>(g_b, 1, nv, v0, cx<V>{dpd, gr2});
+        st_row<V>(g_b, 2, nv, v0, cx<V>{dpha, gphi});
+    } else {
+        const V dmw = vmul(kRhoSc * scale, vfma(x.uW.im, a.sg.im, vmul(x.uW.re, a.sg.re)));
+        const V dmf = vmul(kRhoSc * scale, vfma(x.uF.im, a.sgc.im, vmul(x.uF.re, a.sgc.re)));
+        // 4 pi Re(i rho conj(sg)) = -4 pi (rho.im sg.re - rho.re sg.im)
+        const V dpw = vmul(-2.0f * kTwoPi * scale, vfma(vneg(x.rhoW.re), a.sg.im, vmul(x.rhoW.im, a.sg.re)));
+        const V dpf = vmul(-2.0f * kTwoPi * scale, vfma(vneg(x.rhoF.re), a.sgc.im, vmul(x.rhoF.im, a.sgc.re)));
+        const V dbip = vmul(-2.0f * kTwoPi * scale, a.bq);
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            float *r0 = g_b + (static_cast<size_t>(v0) + l) * rows_or_ch;
+            float *r1 = r0 + static_cast<size_t>(nv) * rows_or_ch;
+            if (rows_or_ch == 4) {
+                __stcs(reinterpret_cast<float4 *>(r0), make_float4(lane_get(dmw, l), lane_get(dmf, l), lane_get(gr2, l), 0.f));
+                __stcs(reinterpret_cast<float4 *>(r1), make_float4(lane_get(dpw, l), lane_get(dpf, l), lane_get(gphi, l), lane_get(dbip, l)));
+            } else {
+                __stcs(r0, lane_get(dmw, l)); __stcs(r0 + 1, lane_get(dmf, l)); __stcs(r0 + 2, lane_get(gr2, l));
+                __stcs(r1, lane_get(dpw, l)); __stcs(r1 + 1, lane_get(dpf, l)); __stcs(r1 + 2, lane_get(gphi, l));
+            }
+        }
+    }
+}
+
+template <int NE, typename V, int MODEL, int MODE>
+__global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    const bool active = v0 < p.nv;
+    float loss_part = 0.f;
+    if (active) {
+        const int nv = p.nv, ne = p.ne;
+        const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * p.rows_or_ch
+                                                            : static_cast<size_t>(p.rows_or_ch) * nv * 2;
+        const Voxel<V> x = decode<V, MODEL>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags);
+        const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+        Adj<V> a;
+        a.sg = czero<V>(); a.sgc = czero<V>(); a.tq = czero<V>(); a.q = czero<V>(); a.bq = splat<V>(0.f);
+        V lsum = splat<V>(0.f);
+        // issue every upstream / measurement load before the math so each thread has ne loads in flight
+        cx<V> in[NE];
+        if constexpr (MODE != MODE_FWD) {
+            const float *src = (MODE == MODE_BWD ? p.gout : p.acqs) + acq_b;
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (e < ne) in[e] = ld_cx(src + static_cast<size_t>(e) * nv * 2, v0, V{});
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                V c, s;
+                unit_phasor(vfma(T.sgn[e], x.bturn, vmul(T.kphi[e], x.phi_t)), c, s);
+                const V d = fast_ex2(vmul(T.kdec[e], x.r2));
+                const cx<V> w{vmul(d, c), vmul(d, s)};
+                const cx<V> yhat = caffine(x.rhoW, T.c_re[e], T.c_im[e], x.rhoF);
+                const cx<V> shat = cmulv(w, yhat);
+                if constexpr (MODE == MODE_FWD) {
+                    st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                } else {
+                    cx<V> G;
+                    if constexpr (MODE == MODE_BWD) {
+                        G = in[e];
+                    } else {
+                        G = cx<V>{mask_sub(shat.re, in[e].re), mask_sub(shat.im, in[e].im)};
+                        lsum = vfma(G.re, G.re, lsum);
+                        lsum = vfma(G.im, G.im, lsum);
+                        if (p.out) st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                    }
+                    const cx<V> g = cmulc(w, G);
+                    a.sg.re = vadd(a.sg.re, g.re);
+                    a.sg.im = vadd(a.sg.im, g.im);
+                    cmac(a.sgc, T.c_re[e], -T.c_im[e], g);
+                    const cx<V> q = cmulc(g, yhat);
+                    a.tq.re = vfma(T.te[e], q.re, a.tq.re);
+                    a.tq.im = vfma(T.te[e], q.im, a.tq.im);
+                    if constexpr (MODEL == IG_MODEL_FFPD) { a.q.re = vadd(a.q.re, q.re); a.q.im = vadd(a.q.im, q.im); }
+                    if constexpr (MODEL != IG_MODEL_FFPD) a.bq = vfma(T.sgn[e], q.im, a.bq);
+                }
+            }
+        }
+        if constexpr (MODE != MODE_FWD) {
+            const float scale = (MODE == MODE_LOSS) ? 2.0f * p.inv_n : 1.0f;
+            write_grads<V, MODEL>(p.gmaps + b * map_elems, p.rows_or_ch, nv, v0, p.flags, x, a, p.r2_sc, scale);
+        }
+        loss_part = hsum(lsum);
+    }
+    if constexpr (MODE == MODE_LOSS) block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+}
+
+template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaStream_t st) {
+    bool packed = (p.nv % 2 == 0) && aligned16(p.maps) && (MODE == MODE_FWD ? aligned16(p.out) : aligned16(p.gmaps));
+    if (MODE == MODE_BWD) packed = packed && aligned16(p.gout);
+    if (MODE == MODE_LOSS) packed = packed && aligned16(p.acqs) && (!p.out || aligned16(p.out));
+    if (MODEL == IG_MODEL_MAGPHA && p.rows_or_ch == 4) {     // 4-channel rows are read/written as float4 in both paths
+        IG_REQUIRE(aligned16(p.maps) && (MODE == MODE_FWD || aligned16(p.gmaps)), IG_E_ALIGN, "mag/phase maps must be 16-byte aligned");
+    }
+    return dispatch_ne(p.ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (packed) {
+            ideal_kernel<NE, pk, MODEL, MODE><<<grid_for(p.nb, p.nv, 2), kThreads, 0, st>>>(p);
+        } else {
+            ideal_kernel<NE, float, MODEL, MODE><<<grid_for(p.nb, p.nv, 1), kThreads, 0, st>>>(p);
+        }
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+template <int MODE> static int launch_model(int model, const FwdParams &p, cudaStream_t st) {
+    switch (model) {
+        case IG_MODEL_WFPM: return launch_ideal<IG_MODEL_WFPM, MODE>(p, st);
+        case IG_MODEL_FFPD: return launch_ideal<IG_MODEL_FFPD, MODE>(p, st);
+        case IG_MODEL_MAGPHA: return launch_ideal<IG_MODEL_MAGPHA, MODE>(p, st);
+    }
+    set_error("unknown model %d", model);
+    return IG_E_ARG;
+}
+
+static int check_model_args(const char *fn, int model, int rows_or_ch, int nb, int ne, int nv) {
+    IG_REQUIRE(nb > 0 && nv > 0 && nb <= 65535, IG_E_ARG, "%s: nb=%d (1..65535), nv=%d", fn, nb, nv);
+    IG_REQUIRE(ne >= 1 && ne <= IG_MAX_NE, IG_E_NE, "%s: ne=%d outside [1, %d]", fn, ne, IG_MAX_NE);
+    const bool ok = (model == IG_MODEL_WFPM && (rows_or_ch == 3 || rows_or_ch == 4)) || (model == IG_MODEL_FFPD && rows_or_ch == 3) ||
+                    (model == IG_MODEL_MAGPHA && (rows_or_ch == 3 || rows_or_ch == 4));
+    IG_REQUIRE(ok, IG_E_ARG, "%s: model %d does not take rows/channels = %d", fn, model, rows_or_ch);
+    return 0;
+}
+
+}  // namespace ig
+
+using namespace ig;
+
+extern "C" int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv, float r2_sc,
+                            int flags, float *out_d, void *stream) {
+    IG_REQUIRE(maps_d && tab_d && out_d, IG_E_ARG, "ig_ideal_fwd: null pointer");
+    if (int rc = check_model_args("ig_ideal_fwd", model, rows_or_ch, nb, ne, nv)) return rc;
+    FwdParams p{};
+    p.maps = maps_d; p.tab = tab_d; p.out = out_d; p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv; p.flags = flags; p.r2_sc = r2_sc;
+    return launch_model<MODE_FWD>(model, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ig_ideal_bwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv, float r2_sc,
+                            int flags, const float *gout_d, float *gmaps_d, void *stream) {
+    IG_REQUIRE(maps_d && tab_d && gout_d && gmaps_d, IG_E_ARG, "ig_ideal_bwd: null pointer");
+    if (int rc = check_model_args("ig_ideal_bwd", model, rows_or_ch, nb, ne, nv)) return rc;
+    FwdParams p{};
+    p.maps = maps_d; p.tab = tab_d; p.gout = gout_d; p.gmaps = gmaps_d; p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv;
+    p.flags = flags; p.r2_sc = r2_sc;
+    return launch_model<MODE_BWD>(model, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ig_ideal_loss(int model, const float *maps_d, int rows_or_ch, const float *acqs_d, const float *tab_d, int nb, int ne,
+                             int nv, float r2_sc, int flags, float inv_n, float *gmaps_d, float *shat_d, float *loss_d, void *scratch_d,
+                             size_t scratch_bytes, void *stream) {
+    IG_REQUIRE(maps_d && tab_d && acqs_d && gmaps_d && loss_d && scratch_d, IG_E_ARG, "ig_ideal_loss: null pointer");
+    if (int rc = check_model_args("ig_ideal_loss", model, rows_or_ch, nb, ne, nv)) return rc;
+    IG_REQUIRE(scratch_bytes >= ig_loss_scratch_bytes(nb, nv), IG_E_SCRATCH, "ig_ideal_loss: scratch %zu < %zu bytes", scratch_bytes,
+               ig_loss_scratch_bytes(nb, nv));
+    FwdParams p{};
+    p.maps = maps_d; p.tab = tab_d; p.acqs = acqs_d; p.gmaps = gmaps_d; p.out = shat_d; p.loss = loss_d; p.scratch = scratch_d;
+    p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv; p.flags = flags; p.r2_sc = r2_sc; p.inv_n = inv_n;
+    return launch_model<MODE_LOSS>(model, p, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,634 @@
+// Least-squares water/fat solve (get_rho), project-and-resynthesise (acq_to_acq), their adjoints, and the
+// fused config-2 physics objective.
+//
+// Replaces get_rho / acq_to_acq of the reference (/root/reference/wflib/IDEAL_model.py:527-624, 142-200)
+// and TF autodiff through them (train-IDEAL-unsup.py:214-218,236,255; train-IDEAL-TEaug.py:304).
+// Per voxel, with y_e = Wm_e S_e the demodulated echoes (Wm_e = exp(+te_e R - i(2 pi te_e phi + s_e beta))):
+//     rho = M^+ y          yhat = M rho          S_hat_e = Wp_e yhat_e         (Wp_e = 1 / Wm_e)
+// The pseudo-inverse M^+ depends only on the sample's echo times, so it is a shared-memory table and the
+// "solve" is a 2 x ne complex contraction held in registers.
+#include "ig_common.cuh"
+
+namespace ig {
+
+struct SolveParams {
+    const float *acqs, *pm, *bip, *tab;
+    const float *g_rho, *g_demod, *g_shat;
+    float *rho, *demod, *shat;
+    float *g_acqs, *g_pm, *g_bip;
+    float *loss;
+    void *scratch;
+    long pm_bstride, bip_bstride;
+    int nb, ne, nv, flags;
+    float r2_sc, inv_n;
+};
+
+// echo loads / stores for both acquisition layouts
+template <typename V, bool FLAT> __device__ __forceinline__ cx<V> ld_echo(const float *acq_b, int e, int ne, int nv, int v0) {
+    if constexpr (!FLAT) {
+        return ld_cx(acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
+    } else {
+        cx<V> z;
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            const float2 t = __ldcs(reinterpret_cast<const float2 *>(acq_b + (static_cast<size_t>(v0) + l) * 2 * ne) + e);
+            lane_set(z.re, l, t.x);
+            lane_set(z.im, l, t.y);
+        }
+        return z;
+    }
+}
+template <typename V, bool FLAT> __device__ __forceinline__ void st_echo(float *acq_b, int e, int ne, int nv, int v0, const cx<V> &z) {
+    if constexpr (!FLAT) {
+        st_cx(acq_b + static_cast<size_t>(e) * nv * 2, v0, z);
+    } else {
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l)
+            __stcs(reinterpret_cast<float2 *>(acq_b + (static_cast<size_t>(v0) + l) * 2 * ne) + e, make_float2(lane_get(z.re, l), lane_get(z.im, l)));
+    }
+}
+
+// (phi map, R2 map) of a voxel; the flat layout stores (R2*, phi) (IDEAL_model.py:559-560)
+template <typename V, bool FLAT> __device__ __forceinline__ void ld_pm(const float *pm_b, int v0, V &phi_t, V &r2) {
+    const cx<V> m = ld_cx(pm_b, v0, V{});
+    if constexpr (FLAT) { phi_t = m.im; r2 = m.re; } else { phi_t = m.re; r2 = m.im; }
+}
+
+// demodulator for one echo: Wm = dinv * conj(u), Wp = d * u
+template <typename V> struct Mod {
+    V c, s, d, dinv;
+};
+template <int NE, typename V> __device__ __forceinline__ Mod<V> modulator(const SampleTab<NE> &T, int e, V phi_t, V r2, V bturn) {
+    Mod<V> m;
+    unit_phasor(vfma(T.sgn[e], bturn, vmul(T.kphi[e], phi_t)), m.c, m.s);
+    const V lg = vmul(T.kdec[e], r2);
+    m.d = fast_ex2(lg);
+    m.dinv = fast_ex2(vneg(lg));
+    return m;
+}
+template <typename V> __device__ __forceinline__ cx<V> demod(const Mod<V> &m, const cx<V> &S) {       // Wm S
+    const cx<V> t{vfma(m.s, S.im, vmul(m.c, S.re)), vfma(vneg(m.s), S.re, vmul(m.c, S.im))};
+    return cscale(m.dinv, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> remod(const Mod<V> &m, const cx<V> &y) {       // Wp y
+    const cx<V> t{vfma(vneg(m.s), y.im, vmul(m.c, y.re)), vfma(m.s, y.re, vmul(m.c, y.im))};
+    return cscale(m.d, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> remod_inv(const Mod<V> &m, const cx<V> &g) {   // conj(Wm) g = dinv u g
+    const cx<V> t{vfma(vneg(m.s), g.im, vmul(m.c, g.re)), vfma(m.s, g.re, vmul(m.c, g.im))};
+    return cscale(m.dinv, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> demod_fwd(const Mod<V> &m, const cx<V> &G) {   // conj(Wp) G = d conj(u) G
+    const cx<V> t{vfma(m.s, G.im, vmul(m.c, G.re)), vfma(vneg(m.s), G.re, vmul(m.c, G.im))};
+    return cscale(m.d, t);
+}
+
+// half-angle helpers for the phase-constrained solve: theta = 0.5 arg(z) -> (cos theta, sin theta)
+__device__ __forceinline__ void half_angle(float zr, float zi, float &ct, float &st) {
+    const float th = 0.5f * atan2f(zi, zr);
+    sincosf(th, &st, &ct);
+}
+
+// =================================================================================================
+// get_rho forward
+// =================================================================================================
+template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThreads) get_rho_fwd_kernel(const SolveParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    if (v0 >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    cx<V> S[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = ld_echo<V, FLAT>(p.acqs + acq_b, e, ne, nv, v0);
+    V phi_t, r2, bturn = splat<V>(0.f);
+    ld_pm<V, FLAT>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+    if (p.bip) bturn = vmul(0.5f, ld_cx(p.bip + b * p.bip_bstride, v0, V{}).re);
+    cx<V> rw = czero<V>(), rf = czero<V>();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const Mod<V> m = modulator(T, e, phi_t, r2, bturn);
+            const cx<V> y = demod(m, S[e]);
+            if (p.demod) st_cx(p.demod + acq_b + static_cast<size_t>(e) * nv * 2, v0, y);
+            cmac(rw, T.pw_re[e], T.pw_im[e], y);
+            cmac(rf, T.pf_re[e], T.pf_im[e], y);
+        }
+    }
+    if (p.flags & IG_F_PHASE_CONSTRAINT) {
+        // theta = 0.5 arg(rho_W^2 + rho_F^2) (H^+ = Re(M^+ M)^+ is the identity to rounding, :64-68,584-592);
+        // rho_s <- Re(rho_s e^{-i theta}) e^{i theta}
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            const float wr = lane_get(rw.re, l), wi = lane_get(rw.im, l), fr = lane_get(rf.re, l), fi = lane_get(rf.im, l);
+            float ct, st;
+            half_angle(wr * wr - wi * wi + fr * fr - fi * fi, 2.f * (wr * wi + fr * fi), ct, st);
+            const float mw = wr * ct + wi * st, mf = fr * ct + fi * st;
+            lane_set(rw.re, l, mw * ct); lane_set(rw.im, l, mw * st);
+            lane_set(rf.re, l, mf * ct); lane_set(rf.im, l, mf * st);
+        }
+    }
+    const float inv = 1.0f / kRhoSc;
+    rw = cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)};
+    rf = cx<V>{vmul(inv, rf.re), vmul(inv, rf.im)};
+    if constexpr (!FLAT) {
+        float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+        st_cx(rho_b, v0, rw);
+        st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, rf);
+    } else {
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l)
+            __stcs(reinterpret_cast<float4 *>(p.rho + (static_cast<size_t>(b) * nv + v0 + l) * 4),
+                   make_float4(lane_get(rw.re, l), lane_get(rw.im, l), lane_get(rf.re, l), lane_get(rf.im, l)));
+    }
+}
+
+// =================================================================================================
+// get_rho backward (unconstrained solve).  With gy_e = sum_s conj(M^+[s,e]) g_rho_s / rho_sc + g_demod_e:
+//   dL/dS_e = conj(Wm_e) gy_e ;  X = sum_e te_e conj(gy_e) y_e ;  B = sum_e s_e Im(conj(gy_e) y_e)
+//   dL/dphi~ = 2 pi fm_sc Im X ;  dL/dR~ = r2_sc Re X ;  dL/db~ = pi B
+// =================================================================================================
+template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThreads) get_rho_bwd_kernel(const SolveParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    if (v0 >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    cx<V> S[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = ld_echo<V, FLAT>(p.acqs + acq_b, e, ne, nv, v0);
+    V phi_t, r2, bturn = splat<V>(0.f);
+    ld_pm<V, FLAT>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+    if (p.bip) bturn = vmul(0.5f, ld_cx(p.bip + b * p.bip_bstride, v0, V{}).re);
+    cx<V> gw = czero<V>(), gf = czero<V>();
+    if (p.g_rho) {
+        const float inv = 1.0f / kRhoSc;
+        if constexpr (!FLAT) {
+            const float *g_b = p.g_rho + static_cast<size_t>(b) * 2 * nv * 2;
+            gw = ld_cx(g_b, v0, V{});
+            gf = ld_cx(g_b + static_cast<size_t>(nv) * 2, v0, V{});
+        } else {
+#pragma unroll
+            for (int l = 0; l < lanes<V>::n; ++l) {
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(p.g_rho + (static_cast<size_t>(b) * nv + v0 + l) * 4));
+                lane_set(gw.re, l, t.x); lane_set(gw.im, l, t.y); lane_set(gf.re, l, t.z); lane_set(gf.im, l, t.w);
+            }
+        }
+        gw = cx<V>{vmul(inv, gw.re), vmul(inv, gw.im)};
+        gf = cx<V>{vmul(inv, gf.re), vmul(inv, gf.im)};
+    }
+    cx<V> X = czero<V>();
+    V B = splat<V>(0.f);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const Mod<V> m = modulator(T, e, phi_t, r2, bturn);
+            const cx<V> y = demod(m, S[e]);
+            cx<V> gy = czero<V>();
+            cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
+            cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+            if (p.g_demod) {
+                const cx<V> gd = ld_cx(p.g_demod + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
+                gy.re = vadd(gy.re, gd.re);
+                gy.im = vadd(gy.im, gd.im);
+            }
+            if (p.g_acqs) st_echo<V, FLAT>(p.g_acqs + acq_b, e, ne, nv, v0, remod_inv(m, gy));
+            const cx<V> q = cmulc(gy, y);
+            X.re = vfma(T.te[e], q.re, X.re);
+            X.im = vfma(T.te[e], q.im, X.im);
+            B = vfma(T.sgn[e], q.im, B);
+        }
+    }
+    const V gphi = vmul(kTwoPi * kFmSc, X.im), gr2 = vmul(p.r2_sc, X.re);
+    float *gpm_b = p.g_pm + static_cast<size_t>(b) * nv * 2;
+    st_cx(gpm_b, v0, FLAT ? cx<V>{gr2, gphi} : cx<V>{gphi, gr2});
+    if (p.g_bip) st_cx(p.g_bip + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(0.5f * kTwoPi, B), splat<V>(0.f)});
+}
+
+// =================================================================================================
+// acq_to_acq forward: rho_hat / rho_sc and S_hat (or |S_hat|)
+// =================================================================================================
+template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_fwd_kernel(const SolveParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    if (v0 >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    cx<V> S[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
+    V phi_t, r2;
+    ld_pm<V, false>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+    const V zero = splat<V>(0.f);
+    Mod<V> m[NE];
+    cx<V> rw = czero<V>(), rf = czero<V>();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            m[e] = modulator(T, e, phi_t, r2, zero);
+            const cx<V> y = demod(m[e], S[e]);
+            cmac(rw, T.pw_re[e], T.pw_im[e], y);
+            cmac(rf, T.pf_re[e], T.pf_im[e], y);
+        }
+    }
+    if (p.rho) {
+        const float inv = 1.0f / kRhoSc;
+        float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+        st_cx(rho_b, v0, cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)});
+        st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<V>{vmul(inv, rf.re), vmul(inv, rf.im)});
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const cx<V> sh = remod(m[e], caffine(rw, T.c_re[e], T.c_im[e], rf));
+            if (p.flags & IG_F_ONLY_MAG) {
+                st_real(p.shat + static_cast<size_t>(b) * ne * nv + static_cast<size_t>(e) * nv, v0, vsqrt(vfma(sh.re, sh.re, vmul(sh.im, sh.im))));
+            } else {
+                st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, sh);
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// acq_to_acq backward.  Upstream G_e on S_hat (or g_e on |S_hat|: G = g S_hat / |S_hat|) and Gamma_s on rho/rho_sc.
+//   v_e = conj(Wp_e) G_e ; g_rho = Gamma / rho_sc + M^H v ; gy = (M^+)^H g_rho ; dL/dS_e = conj(Wm_e) gy_e
+//   X = sum_e te_e (conj(gy_e) y_e - conj(v_e) yhat_e) ; dL/dphi~ = 2 pi fm_sc Im X ; dL/dR~ = r2_sc Re X
+// =================================================================================================
+template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bwd_kernel(const SolveParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    if (v0 >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    const V zero = splat<V>(0.f);
+    V phi_t, r2;
+    ld_pm<V, false>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+    Mod<V> m[NE];
+    cx<V> y[NE];
+    cx<V> rw = czero<V>(), rf = czero<V>();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            m[e] = modulator(T, e, phi_t, r2, zero);
+            y[e] = demod(m[e], ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{}));
+            cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
+            cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
+        }
+    }
+    // pass over the upstream of S_hat: v_e, M^H v, and the -conj(v) yhat part of X
+    cx<V> gw = czero<V>(), gf = czero<V>(), X = czero<V>();
+    if (p.g_shat) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const cx<V> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
+                cx<V> G;
+                if (p.flags & IG_F_ONLY_MAG) {
+                    // |S_hat| = d |yhat| ; G = g S_hat / |S_hat| ; v = conj(Wp) G = g d yhat / |yhat|  (0 where |yhat| = 0)
+                    const V g = ld_real(p.g_shat + static_cast<size_t>(b) * ne * nv + static_cast<size_t>(e) * nv, v0, V{});
+                    V sc = zero;
+#pragma unroll
+                    for (int l = 0; l < lanes<V>::n; ++l) {
+                        const float a2 = lane_get(yhat.re, l) * lane_get(yhat.re, l) + lane_get(yhat.im, l) * lane_get(yhat.im, l);
+                        lane_set(sc, l, a2 > 0.f ? lane_get(g, l) * lane_get(m[e].d, l) * rsqrtf(a2) : 0.f);
+                    }
+                    G = cscale(sc, yhat);            // this is v_e directly
+                } else {
+                    G = demod_fwd(m[e], ld_cx(p.g_shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{}));
+                }
+                const cx<V> v = G;
+                gw.re = vadd(gw.re, v.re);
+                gw.im = vadd(gw.im, v.im);
+                cmac(gf, T.c_re[e], -T.c_im[e], v);
+                const cx<V> q = cmulc(v, yhat);
+                X.re = vfma(-T.te[e], q.re, X.re);
+                X.im = vfma(-T.te[e], q.im, X.im);
+            }
+        }
+    }
+    if (p.g_rho) {
+        const float inv = 1.0f / kRhoSc;
+        const float *g_b = p.g_rho + static_cast<size_t>(b) * 2 * nv * 2;
+        const cx<V> a = ld_cx(g_b, v0, V{}), c = ld_cx(g_b + static_cast<size_t>(nv) * 2, v0, V{});
+        gw.re = vfma(inv, a.re, gw.re); gw.im = vfma(inv, a.im, gw.im);
+        gf.re = vfma(inv, c.re, gf.re); gf.im = vfma(inv, c.im, gf.im);
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            cx<V> gy = czero<V>();
+            cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
+            cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+            if (p.g_acqs) st_cx(p.g_acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod_inv(m[e], gy));
+            const cx<V> q = cmulc(gy, y[e]);
+            X.re = vfma(T.te[e], q.re, X.re);
+            X.im = vfma(T.te[e], q.im, X.im);
+        }
+    }
+    st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(kTwoPi * kFmSc, X.im), vmul(p.r2_sc, X.re)});
+}
+
+// =================================================================================================
+// Fused config-2 objective: loss = inv_n sum |mask(S_hat) - A|^2 and d loss / d (phi~, R~).
+//
+// Fast path (every voxel of the warp is either fully non-zero or fully zero, the only cases real,
+// body-masked data produce): the residual is taken in the demodulated frame, r = yhat - y, so that
+//     S_hat - A = Wp r,     loss = sum_e d_e^2 |r_e|^2,     K = sum_e d_e^2 conj(r_e) (te_e yhat_e - h_e),
+//     h = M M^+ (te . y),   dL/dphi~ = -fm_sc (4 pi / N) Im K,   dL/dR~ = -r2_sc (2 / N) Re K
+// which needs neither Wp nor a second contraction with M^+ (derivation in DESIGN.md).
+// Slow path (some component exactly zero while others are not): the mask is applied per real/imag
+// component exactly as the reference does (train-IDEAL-unsup.py:218) with the general adjoint.
+// =================================================================================================
+template <int NE>
+__device__ __noinline__ void a2a_loss_slow_voxel(const SampleTab<NE> &T, const float *acq_b, int ne, int nv, int v, float phi_t, float r2,
+                                                 float r2_sc, float &loss, float &gphi, float &gr2) {
+    cx<float> y[NE], vv[NE];
+    Mod<float> m[NE];
+    cx<float> rw = czero<float>(), rf = czero<float>();
+    for (int e = 0; e < ne; ++e) {
+        m[e] = modulator(T, e, phi_t, r2, 0.f);
+        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
+        y[e] = demod(m[e], cx<float>{s.x, s.y});
+        cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
+        cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
+    }
+    cx<float> gw = czero<float>(), gf = czero<float>(), X = czero<float>();
+    loss = 0.f;
+    for (int e = 0; e < ne; ++e) {
+        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
+        const cx<float> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
+        const cx<float> sh = remod(m[e], yhat);
+        const cx<float> E{mask_sub(sh.re, s.x), mask_sub(sh.im, s.y)};
+        loss += E.re * E.re + E.im * E.im;
+        vv[e] = demod_fwd(m[e], E);
+        gw.re += vv[e].re;
+        gw.im += vv[e].im;
+        cmac(gf, T.c_re[e], -T.c_im[e], vv[e]);
+        const cx<float> q = cmulc(vv[e], yhat);
+        X.re = fmaf(-T.te[e], q.re, X.re);
+        X.im = fmaf(-T.te[e], q.im, X.im);
+    }
+    for (int e = 0; e < ne; ++e) {
+        cx<float> gy = czero<float>();
+        cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
+        cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+        const cx<float> q = cmulc(gy, y[e]);
+        X.re = fmaf(T.te[e], q.re, X.re);
+        X.im = fmaf(T.te[e], q.im, X.im);
+    }
+    gphi = kTwoPi * kFmSc * X.im;      // caller applies 2 / N
+    gr2 = r2_sc * X.re;
+}
+
+template <int NE, typename V, bool OUTPUTS> __global__ void __launch_bounds__(kThreads) a2a_loss_kernel(const SolveParams p) {
+    __shared__ SampleTab<NE> T;
+    __shared__ float tpw_re[NE], tpw_im[NE], tpf_re[NE], tpf_im[NE];   // te * M^+ rows
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    if (threadIdx.x < NE) {
+        const int e = threadIdx.x;
+        tpw_re[e] = T.te[e] * T.pw_re[e]; tpw_im[e] = T.te[e] * T.pw_im[e];
+        tpf_re[e] = T.te[e] * T.pf_re[e]; tpf_im[e] = T.te[e] * T.pf_im[e];
+    }
+    __syncthreads();
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    const bool active = v0 < p.nv;
+    const int nv = p.nv, ne = p.ne;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    float loss_part = 0.f;
+    bool ragged = false;      // a voxel with some, but not all, components exactly zero
+    cx<V> y[NE];
+    V phi_t = splat<V>(0.f), r2 = splat<V>(0.f);
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            if (e < ne) y[e] = ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
+        ld_pm<V, false>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            int nz = 0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (e < ne) nz += (lane_get(y[e].re, l) != 0.f) + (lane_get(y[e].im, l) != 0.f);
+            ragged |= (nz != 0 && nz != 2 * ne);
+        }
+    }
+    const bool warp_ragged = __any_sync(0xffffffffu, ragged);
+    if (active && !warp_ragged) {
+        const V zero = splat<V>(0.f);
+        V d2[NE];
+        cx<V> rw = czero<V>(), rf = czero<V>(), tw = czero<V>(), tf = czero<V>();
+        [[maybe_unused]] Mod<V> mods[OUTPUTS ? NE : 1];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const Mod<V> m = modulator(T, e, phi_t, r2, zero);
+                if constexpr (OUTPUTS) mods[e] = m;
+                d2[e] = vmul(m.d, m.d);
+                y[e] = demod(m, y[e]);
+                cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
+                cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
+                cmac(tw, tpw_re[e], tpw_im[e], y[e]);
+                cmac(tf, tpf_re[e], tpf_im[e], y[e]);
+            }
+        }
+        V lsum = zero;
+        cx<V> K = czero<V>();
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const cx<V> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
+                const cx<V> h = caffine(tw, T.c_re[e], T.c_im[e], tf);
+                const cx<V> r{vsub(yhat.re, y[e].re), vsub(yhat.im, y[e].im)};
+                const cx<V> w{vmul(d2[e], r.re), vmul(d2[e], r.im)};                      // d^2 r
+                lsum = vfma(w.re, r.re, lsum);
+                lsum = vfma(w.im, r.im, lsum);
+                const cx<V> g{vfma(T.te[e], yhat.re, vneg(h.re)), vfma(T.te[e], yhat.im, vneg(h.im))};
+                const cx<V> q = cmulc(w, g);                                              // d^2 conj(r) (te yhat - h)
+                K.re = vadd(K.re, q.re);
+                K.im = vadd(K.im, q.im);
+                if constexpr (OUTPUTS) {
+                    if (p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod(mods[e], yhat));
+                }
+            }
+        }
+        loss_part = hsum(lsum);
+        const cx<V> g{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * p.r2_sc * p.inv_n, K.re)};
+        st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, g);
+        if constexpr (OUTPUTS) {
+            if (p.rho) {
+                const float inv = 1.0f / kRhoSc;
+                float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                st_cx(rho_b, v0, cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)});
+                st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<V>{vmul(inv, rf.re), vmul(inv, rf.im)});
+            }
+        }
+    } else if (active) {
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            float ls, gphi, gr2;
+            a2a_loss_slow_voxel<NE>(T, p.acqs + acq_b, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2, l), p.r2_sc, ls, gphi, gr2);
+            loss_part += ls;
+            reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+        }
+        if constexpr (OUTPUTS) {
+            // materialised outputs do not depend on the mask: recompute them with the plain forward formulas
+            const V zero = splat<V>(0.f);
+            cx<V> rw = czero<V>(), rf = czero<V>();
+            Mod<V> mods[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (e < ne) {
+                    mods[e] = modulator(T, e, phi_t, r2, zero);
+                    const cx<V> ye = demod(mods[e], y[e]);
+                    cmac(rw, T.pw_re[e], T.pw_im[e], ye);
+                    cmac(rf, T.pf_re[e], T.pf_im[e], ye);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (e < ne && p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod(mods[e], caffine(rw, T.c_re[e], T.c_im[e], rf)));
+            if (p.rho) {
+                const float inv = 1.0f / kRhoSc;
+                float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                st_cx(rho_b, v0, cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)});
+                st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<V>{vmul(inv, rf.re), vmul(inv, rf.im)});
+            }
+        }
+    }
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+}
+
+// -------------------------------------------------------------------------------------------------
+// launch helpers
+// -------------------------------------------------------------------------------------------------
+static int check_common(const char *fn, int nb, int ne, int nv, int min_ne) {
+    IG_REQUIRE(nb > 0 && nv > 0 && nb <= 65535, IG_E_ARG, "%s: nb=%d (1..65535), nv=%d", fn, nb, nv);
+    IG_REQUIRE(ne >= min_ne && ne <= IG_MAX_NE, IG_E_NE, "%s: ne=%d outside [%d, %d]", fn, ne, min_ne, IG_MAX_NE);
+    return 0;
+}
+
+template <typename K1, typename K2> static int launch_pair(bool packed, const SolveParams &p, cudaStream_t st, K1 kp, K2 ks) {
+    if (packed) {
+        kp<<<grid_for(p.nb, p.nv, 2), kThreads, 0, st>>>(p);
+    } else {
+        ks<<<grid_for(p.nb, p.nv, 1), kThreads, 0, st>>>(p);
+    }
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static bool all_aligned(std::initializer_list<const void *> ps) {
+    for (const void *q : ps)
+        if (q && !aligned16(q)) return false;
+    return true;
+}
+
+}  // namespace ig
+
+using namespace ig;
+
+extern "C" int ig_get_rho_fwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
+                              const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, float *rho_d, float *demod_d, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && rho_d, IG_E_ARG, "ig_get_rho_fwd: null pointer");
+    if (int rc = check_common("ig_get_rho_fwd", nb, ne, nv, 2)) return rc;
+    const bool flat = flags & IG_F_FLAT;
+    IG_REQUIRE(!(flat && (bip_d || demod_d)), IG_E_UNSUPPORTED, "ig_get_rho_fwd: flat layout has no bipolar / demod output");
+    IG_REQUIRE(!flat || aligned16(rho_d), IG_E_ALIGN, "ig_get_rho_fwd: flat rho output must be 16-byte aligned");
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.bip = bip_d; p.bip_bstride = bip_bstride; p.tab = tab_d;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.flags = flags; p.rho = rho_d; p.demod = demod_d;
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, bip_d, rho_d, demod_d});
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (flat) return launch_pair(packed, p, st, get_rho_fwd_kernel<NE, pk, true>, get_rho_fwd_kernel<NE, float, true>);
+        return launch_pair(packed, p, st, get_rho_fwd_kernel<NE, pk, false>, get_rho_fwd_kernel<NE, float, false>);
+    });
+}
+
+extern "C" int ig_get_rho_bwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
+                              const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, const float *g_rho_d,
+                              const float *g_demod_d, float *g_acqs_d, float *g_pm_d, float *g_bip_d, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && g_pm_d, IG_E_ARG, "ig_get_rho_bwd: null pointer");
+    if (int rc = check_common("ig_get_rho_bwd", nb, ne, nv, 2)) return rc;
+    IG_REQUIRE(!(flags & IG_F_PHASE_CONSTRAINT), IG_E_UNSUPPORTED, "ig_get_rho_bwd: phase-constrained solve has no adjoint kernel");
+    const bool flat = flags & IG_F_FLAT;
+    IG_REQUIRE(!(flat && (bip_d || g_demod_d || g_bip_d)), IG_E_UNSUPPORTED, "ig_get_rho_bwd: flat layout has no bipolar / demod terms");
+    IG_REQUIRE(!flat || !g_rho_d || aligned16(g_rho_d), IG_E_ALIGN, "ig_get_rho_bwd: flat g_rho must be 16-byte aligned");
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.bip = bip_d; p.bip_bstride = bip_bstride; p.tab = tab_d;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.flags = flags; p.g_rho = g_rho_d; p.g_demod = g_demod_d;
+    p.g_acqs = g_acqs_d; p.g_pm = g_pm_d; p.g_bip = g_bip_d;
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 &&
+                        all_aligned({acqs_d, pm_d, bip_d, g_rho_d, g_demod_d, g_acqs_d, g_pm_d, g_bip_d});
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (flat) return launch_pair(packed, p, st, get_rho_bwd_kernel<NE, pk, true>, get_rho_bwd_kernel<NE, float, true>);
+        return launch_pair(packed, p, st, get_rho_bwd_kernel<NE, pk, false>, get_rho_bwd_kernel<NE, float, false>);
+    });
+}
+
+extern "C" int ig_a2a_fwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                          float r2_sc, int flags, float *rho_d, float *shat_d, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && shat_d, IG_E_ARG, "ig_a2a_fwd: null pointer");
+    if (int rc = check_common("ig_a2a_fwd", nb, ne, nv, 2)) return rc;
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    p.flags = flags; p.rho = rho_d; p.shat = shat_d;
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, rho_d, shat_d});
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        return launch_pair(packed, p, st, a2a_fwd_kernel<NE, pk>, a2a_fwd_kernel<NE, float>);
+    });
+}
+
+extern "C" int ig_a2a_bwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                          float r2_sc, int flags, const float *g_rho_d, const float *g_shat_d, float *g_acqs_d, float *g_pm_d, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && g_pm_d, IG_E_ARG, "ig_a2a_bwd: null pointer");
+    if (int rc = check_common("ig_a2a_bwd", nb, ne, nv, 2)) return rc;
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    p.flags = flags; p.g_rho = g_rho_d; p.g_shat = g_shat_d; p.g_acqs = g_acqs_d; p.g_pm = g_pm_d;
+    // the adjoint keeps y_e and the modulators of every echo live: one voxel per thread keeps it at two blocks per SM
+    const bool packed = false;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        return launch_pair(packed, p, st, a2a_bwd_kernel<NE, pk>, a2a_bwd_kernel<NE, float>);
+    });
+}
+
+extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                           float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
+                           size_t scratch_bytes, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && g_pm_d && loss_d && scratch_d, IG_E_ARG, "ig_a2a_loss: null pointer");
+    if (int rc = check_common("ig_a2a_loss", nb, ne, nv, 2)) return rc;
+    IG_REQUIRE(scratch_bytes >= ig_loss_scratch_bytes(nb, nv), IG_E_SCRATCH, "ig_a2a_loss: scratch %zu < %zu bytes", scratch_bytes,
+               ig_loss_scratch_bytes(nb, nv));
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    p.inv_n = inv_n; p.g_pm = g_pm_d; p.rho = rho_d; p.shat = shat_d; p.loss = loss_d; p.scratch = scratch_d;
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, g_pm_d, rho_d, shat_d});
+    const bool outputs = rho_d || shat_d;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (outputs) return launch_pair(packed, p, st, a2a_loss_kernel<NE, pk, true>, a2a_loss_kernel<NE, float, true>);
+        return launch_pair(packed, p, st, a2a_loss_kernel<NE, pk, false>, a2a_loss_kernel<NE, float, false>);
+    });
+}

@@ -1,0 +1,72 @@
+"""ctypes loader for libidealgan.so (the C ABI declared in include/idealgan.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C ideal-gan_b200/csrc`.  There is no
+fallback: if the shared object is missing, or the device is not sm_100, every operator raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidealgan.so")
+
+MAX_NE = 16
+TAB_ROWS = 12
+TAB_FLOATS = TAB_ROWS * MAX_NE
+ROW_TE, ROW_C_RE, ROW_C_IM, ROW_PW_RE, ROW_PW_IM, ROW_PF_RE, ROW_PF_IM, ROW_AP0, ROW_AP1, ROW_AP2, ROW_META = range(11)
+MODEL_WFPM, MODEL_FFPD, MODEL_MAGPHA = 0, 1, 2
+F_PHASE_CONSTRAINT, F_FLAT, F_ONLY_MAG, F_NO_RELU = 1, 2, 4, 8
+
+_fp = C.c_void_p          # device / host float pointers travel as integers
+_i, _f, _l, _sz = C.c_int, C.c_float, C.c_long, C.c_size_t
+
+# name -> (restype, argtypes); one entry per symbol of include/idealgan.h
+SIGNATURES = {
+    "ig_version": (_i, []),
+    "ig_last_error": (C.c_char_p, []),
+    "ig_device_ok": (_i, []),
+    "ig_gen_tables": (_i, [_fp, _i, _i, _f, _fp, _fp]),
+    "ig_gen_tables_host": (_i, [_fp, _i, _i, _f, _fp]),
+    "ig_loss_scratch_bytes": (_sz, [_i, _i]),
+    "ig_ideal_fwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp]),
+    "ig_ideal_bwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
+    "ig_ideal_loss": (_i, [_i, _fp, _i, _fp, _fp, _i, _i, _i, _f, _i, _f, _fp, _fp, _fp, _fp, _sz, _fp]),
+    "ig_get_rho_fwd": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
+    "ig_get_rho_bwd": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "ig_a2a_fwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
+    "ig_a2a_bwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
+    "ig_a2a_loss": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
+    "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),
+    "ig_ctx_destroy": (None, [C.c_void_p]),
+    "ig_a2a_loss_host": (_i, [C.c_void_p, _fp, _fp, _fp, _i, _f, _f, _f, _fp, _fp]),
+}
+
+_lib = None
+
+
+class IdealGanError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IdealGanError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C ideal-gan_b200/csrc`. There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ig_last_error().decode("utf-8", "replace")
+        kind = "invalid argument" if rc < 0 else "CUDA error"
+        raise (ValueError if rc < 0 else IdealGanError)(f"{what}: {kind} {rc}: {msg}")

@@ -1,0 +1,138 @@
+/*
+ * idealgan.h -- C ABI of libidealgan.so: B200 (sm_100a) kernels for the IDEAL water/fat physics path.
+ *
+ * The reference (jpmeneses/IDEAL-GAN) has no FFI: its hot path is TensorFlow op chains inside
+ * wflib/IDEAL_model.py.  Every entry point below therefore replaces one *Python function* of that file
+ * (cited per declaration as IDEAL_model.py:<lines>) and is what the reference-side binding of
+ * INTEGRATION.md (ctypes + DLPack + tf.custom_gradient) calls.
+ *
+ * Conventions
+ *  - All tensors are float32, C-contiguous, in the reference's own layouts (data.py:98-137):
+ *      acquisitions "MEBCRN"  (nb, ne, nv, 2)      nv = H*W, last axis (Re, Im)
+ *      acquisitions "flat"    (nb, nv, 2*ne)       Re/Im interleaved per echo
+ *      maps WF-PM             (nb, rows, nv, 2)    rows = 3 | 4 (row 3 = bipolar phase / pi)
+ *      maps ff/pd/phase       (nb, 3, nv, 2)
+ *      maps mag/phase         (nb, 2, nv, ch)      ch = 3 | 4 (channel 3 of row 1 = bipolar / 4pi)
+ *      PM ("param maps")      row 0 of a (nb, rows>=1, nv, 2) tensor: (phi/300, R2* / r2_sc)
+ *  - Pointers named *_d are DEVICE pointers of the current CUDA device; `stream` is a cudaStream_t
+ *    (NULL = legacy default stream).  Calls are asynchronous on that stream, allocate nothing and keep
+ *    no global mutable state; the only host-side state is a thread-local error string.
+ *  - Per-sample constants (echo times, fat phasor c_e = M[e,1], pseudo-inverse rows) live in a table
+ *    of IG_TAB_FLOATS floats per sample built by ig_gen_tables from the (nb, ne) echo times.
+ *  - Return value: 0 ok; <0 invalid argument (IG_E_*); >0 a cudaError_t.  Never throws.
+ *  - `ne` <= IG_MAX_NE.  Optional outputs may be NULL.
+ */
+#ifndef IDEALGAN_H_
+#define IDEALGAN_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IG_VERSION 100          /* 0.1.0 */
+#define IG_MAX_NE 16
+#define IG_TAB_ROWS 12
+#define IG_TAB_FLOATS (IG_TAB_ROWS * IG_MAX_NE)
+
+/* table rows (each IG_MAX_NE floats, zero padded beyond ne) */
+enum {
+    IG_ROW_TE = 0,      /* echo time [s]                                                        */
+    IG_ROW_C_RE = 1,    /* fat phasor c_e = sum_p alpha_p exp(2 pi i te field f_p)  (M[e,1])     */
+    IG_ROW_C_IM = 2,
+    IG_ROW_PW_RE = 3,   /* pseudo-inverse row for water  M^+[0,e]                                */
+    IG_ROW_PW_IM = 4,
+    IG_ROW_PF_RE = 5,   /* pseudo-inverse row for fat    M^+[1,e]                                */
+    IG_ROW_PF_IM = 6,
+    IG_ROW_AP0 = 7,     /* A^+[0..2, e]: pseudo-inverse of the magnitude design matrix (gen_A)   */
+    IG_ROW_AP1 = 8,
+    IG_ROW_AP2 = 9,
+    IG_ROW_META = 10,   /* [0] = ne, [1] = field                                                 */
+    IG_ROW_RESERVED = 11
+};
+
+enum { IG_MODEL_WFPM = 0, IG_MODEL_FFPD = 1, IG_MODEL_MAGPHA = 2 };
+
+/* flags */
+enum {
+    IG_F_PHASE_CONSTRAINT = 1,  /* get_rho(phase_constraint=True)                                 */
+    IG_F_FLAT = 2,              /* flat layout (MEBCRN=False)                                     */
+    IG_F_ONLY_MAG = 4,          /* acq_to_acq(only_mag=True): second output is |S_hat|, 1 channel  */
+    IG_F_NO_RELU = 8            /* IG_MODEL_WFPM without the relu gate on R2* (not used by wflib) */
+};
+
+enum { IG_E_ARG = -1, IG_E_NE = -2, IG_E_ALIGN = -3, IG_E_SCRATCH = -4, IG_E_UNSUPPORTED = -5 };
+
+int ig_version(void);
+const char *ig_last_error(void);
+/* 1 if the library was built for, and the current device is, compute capability 10.x */
+int ig_device_ok(void);
+
+/* ---- per-sample tables: gen_M / gen_A (IDEAL_model.py:48-97) --------------------------------- */
+/* te_d: (nb, ne) seconds -> tab_d: (nb, IG_TAB_FLOATS).  Arithmetic in fp64, stored fp32. */
+int ig_gen_tables(const float *te_d, int nb, int ne, float field, float *tab_d, void *stream);
+/* same arithmetic on the host (used by the Python gen_M()/gen_A() wrappers for CPU tensors) */
+int ig_gen_tables_host(const float *te_h, int nb, int ne, float field, float *tab_h);
+
+/* ---- loss scratch -------------------------------------------------------------------------- */
+/* Bytes of zero-initialised device scratch the *_loss entry points need for (nb, nv).  The kernels
+ * leave it zeroed again on completion, so one allocation can be reused launch after launch. */
+size_t ig_loss_scratch_bytes(int nb, int nv);
+
+/* ---- forward models: IDEAL_model / IDEAL_mag / IDEAL_mag_phase (IDEAL_model.py:220-299,404-509) */
+/* maps_d layout by model (see top); rows_or_ch = rows (WFPM: 3|4, FFPD: 3) or channels (MAGPHA: 3|4).
+ * out_d: (nb, ne, nv, 2). */
+int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
+                 float r2_sc, int flags, float *out_d, void *stream);
+/* adjoint: gout_d (nb, ne, nv, 2) upstream -> gmaps_d (same shape as maps, every element written) */
+int ig_ideal_bwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
+                 float r2_sc, int flags, const float *gout_d, float *gmaps_d, void *stream);
+/* fused forward -> where(A != 0) mask -> MSE -> backward (train-IDEAL-single.py:154-157,175).
+ * loss_d[0] = inv_n * sum (A - mask(S_hat))^2 ; gmaps_d = d loss / d maps ; shat_d (optional) = unmasked S_hat.
+ * inv_n is 1 / (number of elements of the GLOBAL batch), so shards of a multi-GPU batch sum to the mean. */
+int ig_ideal_loss(int model, const float *maps_d, int rows_or_ch, const float *acqs_d, const float *tab_d,
+                  int nb, int ne, int nv, float r2_sc, int flags, float inv_n, float *gmaps_d, float *shat_d,
+                  float *loss_d, void *scratch_d, size_t scratch_bytes, void *stream);
+
+/* ---- LS water/fat solve: get_rho (IDEAL_model.py:527-624) ------------------------------------- */
+/* pm_d points at the (phi, R2*) row of sample 0; consecutive samples are pm_bstride floats apart.
+ * bip_d (optional, MEBCRN only) points at the bipolar row of sample 0 (its channel 0 is used), stride
+ * bip_bstride.  rho_d: (nb, 2, nv, 2) or flat (nb, nv, 4); demod_d (optional): (nb, ne, nv, 2).
+ * With IG_F_FLAT: acqs (nb, nv, 2ne), pm (nb, nv, 2) ordered (R2*, phi) (IDEAL_model.py:559-560). */
+int ig_get_rho_fwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
+                   const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, float *rho_d,
+                   float *demod_d, void *stream);
+/* adjoint; g_rho_d / g_demod_d upstream (either may be NULL), outputs g_acqs_d (optional), g_pm_d (nb, nv, 2)
+ * dense (row layout of pm, without the batch stride), g_bip_d (optional, (nb, nv, 2), channel 1 = 0). */
+int ig_get_rho_bwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
+                   const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, const float *g_rho_d,
+                   const float *g_demod_d, float *g_acqs_d, float *g_pm_d, float *g_bip_d, void *stream);
+
+/* ---- project + resynthesise: acq_to_acq (IDEAL_model.py:142-200; 2-result form of its callers) -- */
+/* rho_d (optional): (nb, 2, nv, 2) = rho_hat / rho_sc ; shat_d: (nb, ne, nv, 2) or (nb, ne, nv, 1) with ONLY_MAG */
+int ig_a2a_fwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+               float r2_sc, int flags, float *rho_d, float *shat_d, void *stream);
+int ig_a2a_bwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+               float r2_sc, int flags, const float *g_rho_d, const float *g_shat_d, float *g_acqs_d, float *g_pm_d,
+               void *stream);
+/* fused config-2 objective (train-IDEAL-unsup.py:214-218,236,255): acq_to_acq -> mask -> MSE -> d/dPM.
+ * loss_d[0] = inv_n * sum (A - mask(S_hat))^2 ; g_pm_d (nb, nv, 2) ; rho_d / shat_d optional materialisation. */
+int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
+                size_t scratch_bytes, void *stream);
+
+/* ---- host-buffer pipeline (the call timed as `e2e` by bench.py) -------------------------------- */
+/* A context owns device staging buffers and streams on `device`; chunks of `chunk_nb` samples are copied
+ * host->device, processed and copied back with copy/compute overlap.  Host buffers should be pinned. */
+typedef struct ig_ctx ig_ctx;
+int ig_ctx_create(int device, int chunk_nb, int ne, int nv, ig_ctx **out);
+void ig_ctx_destroy(ig_ctx *ctx);
+/* acqs_h (nb, ne, nv, 2), pm_h (nb, 1, nv, 2), te_h (nb, ne) -> loss_h[0], g_pm_h (nb, 1, nv, 2).  Blocking. */
+int ig_a2a_loss_host(ig_ctx *ctx, const float *acqs_h, const float *pm_h, const float *te_h, int nb, float field,
+                     float r2_sc, float inv_n, float *loss_h, float *g_pm_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDEALGAN_H_ */

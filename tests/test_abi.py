@@ -1,0 +1,63 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/idealgan.h declares,
+validates arguments without touching a GPU, and its host table builder (gen_M / gen_A replacement)
+matches the reference's vectors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_close
+from idealgan import _lib as L
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "idealgan.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ig_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    syms = header_symbols()
+    assert len(syms) >= 17
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/idealgan.h but not exported"
+    assert sorted(L.SIGNATURES) == syms, "ctypes signature table out of sync with the header"
+    assert lib.ig_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    lib = L.load()
+    assert lib.ig_gen_tables(0, 1, 6, 1.5, 0, 0) == -1                       # null pointers
+    assert b"null" in lib.ig_last_error()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.addressof(buf)
+    assert lib.ig_gen_tables_host(p, 1, 17, 1.5, p) == -2                    # ne > IG_MAX_NE
+    assert lib.ig_ideal_fwd(0, p, 5, p, 1, 6, 16, 200.0, 0, p, 0) == -1      # rows = 5 is no WF-PM tensor
+    assert lib.ig_a2a_loss(p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, 0, 0, p, p, 8, 0) == -4   # scratch too small
+    assert lib.ig_get_rho_fwd(p, p, 0, 0, 0, p, 1, 1, 16, 200.0, 0, p, 0, 0) == -2        # LS solve needs ne >= 2
+    with pytest.raises(ValueError):
+        L.check(-1, "x")
+
+
+@pytest.mark.parametrize("case", ["orig6_1p5", "rand6_3p0", "rand12_1p5", "rand3_1p5"])
+def test_host_tables_match_reference(golden, case):
+    g = golden("tables")
+    te = np.ascontiguousarray(g[case + "_te"][:, :, 0])
+    nb, ne = te.shape
+    tab = np.zeros((nb, L.TAB_FLOATS), np.float32)
+    L.check(L.load().ig_gen_tables_host(te.ctypes.data, nb, ne, float(g[case + "_field"]), tab.ctypes.data), "tables")
+    t = tab.reshape(nb, L.TAB_ROWS, L.MAX_NE)
+    assert_close(t[:, L.ROW_TE, :ne], te, 0)
+    c = t[:, L.ROW_C_RE, :ne] + 1j * t[:, L.ROW_C_IM, :ne]
+    assert_close(c, g[case + "_M"][:, :, 1], 2e-6, "fat phasor")
+    assert np.all(g[case + "_M"][:, :, 0] == 1)
+    pw = t[:, L.ROW_PW_RE, :ne] + 1j * t[:, L.ROW_PW_IM, :ne]
+    pf = t[:, L.ROW_PF_RE, :ne] + 1j * t[:, L.ROW_PF_IM, :ne]
+    assert_close(np.stack([pw, pf], 1), g[case + "_Mpinv"], 3e-6, "M pinv")
+    ap = t[:, L.ROW_AP0:L.ROW_AP2 + 1, :ne]
+    assert_close(ap, g[case + "_Apinv"], 2e-5 if ne > 3 else 5e-3, "A pinv")     # ne == 3: square, ill-conditioned
+    assert not t[:, :L.ROW_META, ne:].any()                                      # zero padding beyond ne
+    assert np.all(t[:, L.ROW_META, 0] == ne)

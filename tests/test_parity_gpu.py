@@ -1,0 +1,288 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (idealgan.ops -> ctypes -> libidealgan.so),
+against (a) the golden vectors produced by the reference's own source and (b) the CPU oracle on seeded
+inputs.  Tolerance: max|x - ref| <= 1e-5 * max|ref| per tensor (north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from idealgan import _lib as L
+from idealgan import ops, synth
+from oracle import ideal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+MODELS = {"wfpm": L.MODEL_WFPM, "ffpd": L.MODEL_FFPD, "magpha": L.MODEL_MAGPHA}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def cpu(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.requires_grad_(True) if grad else t
+
+
+def test_extension_is_loaded_and_device_is_sm100():
+    lib = L.load()
+    torch.cuda.init()
+    assert lib.ig_device_ok() == 1, "not an sm_100 device"
+    assert any("libidealgan.so" in line for line in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("case", ["orig6_1p5", "rand6_3p0", "rand12_1p5", "rand3_1p5"])
+def test_tables_device_equals_host(golden, case):
+    g = golden("tables")
+    te = np.ascontiguousarray(g[case + "_te"][:, :, 0])
+    nb, ne = te.shape
+    ref = np.zeros((nb, L.TAB_FLOATS), np.float32)
+    L.check(L.load().ig_gen_tables_host(te.ctypes.data, nb, ne, float(g[case + "_field"]), ref.ctypes.data), "host tables")
+    tab = host(ops.gen_tables(dev(g[case + "_te"]), float(g[case + "_field"])))
+    assert_close(tab, ref, 2e-7)
+
+
+FWD = [("wfpm_orig6", "wfpm"), ("wfpm_bip_rand6", "wfpm"), ("wfpm_rand3", "wfpm"), ("wfpm_bip_rand12", "wfpm"),
+       ("ffpd_orig6", "ffpd"), ("ffpd_rand5", "ffpd"), ("magpha_rand6", "magpha"), ("magpha_orig4", "magpha")]
+
+
+@pytest.mark.parametrize("name,model", FWD)
+def test_forward_and_adjoint_vs_reference_vectors(golden, name, model):
+    g = golden("forward")
+    te = g[name + "_te"]
+    ne = te.shape[1]
+    r2 = float(g.get(name + "_r2sc", 200.0))
+    tab = ops.gen_tables(dev(te), float(g[name + "_field"]))
+    maps = dev(g[name + "_maps"])
+    out = ops.ideal_fwd(MODELS[model], maps, tab, ne, r2)
+    assert_close(host(out), g[name + "_out"], TOL, "signal")
+    gm = ops.ideal_bwd(MODELS[model], maps, tab, ne, dev(g[name + "_up"]), r2)
+    assert_close(host(gm), g[name + "_gmaps"], TOL, "grad maps")
+
+
+@pytest.mark.parametrize("model", ["wfpm", "ffpd", "magpha"])
+@pytest.mark.parametrize("ne", [2, 3, 6, 7, 12, 16])
+@pytest.mark.parametrize("hw", [(9, 9), (64, 48)])       # odd voxel count -> scalar path; even -> packed f32x2 path
+def test_forward_and_adjoint_vs_oracle(model, ne, hw):
+    rng = np.random.default_rng(100 + ne)
+    H, W = hw
+    nb = 3
+    bip = ne % 2 == 0
+    if model == "wfpm":
+        maps = synth.wfpm_maps(nb, H, W, rng, bipolar=bip)
+    elif model == "ffpd":
+        maps = synth.ffpd_maps(nb, H, W, rng)
+    else:
+        maps = synth.magpha_maps(nb, H, W, rng, bipolar=bip)
+    te = synth.te_random(nb, ne, rng, d_te_min=0.9e-3 if ne > 8 else 1.6e-3, d_te_d=0.3e-3 if ne > 8 else 1.0e-3)
+    field = 3.0 if ne % 3 == 0 else 1.5
+    fn = {"wfpm": orc.IDEAL_model, "ffpd": orc.IDEAL_mag, "magpha": orc.IDEAL_mag_phase}[model]
+    m = cpu(maps, grad=True)
+    ref = fn(m, [field, cpu(te)], r2_sc=180.0)
+    up = rng.standard_normal(ref.shape).astype(np.float32)
+    (gref,) = torch.autograd.grad((ref * cpu(up)).sum(), [m])
+    tab = ops.gen_tables(dev(te), field)
+    out = ops.ideal_fwd(MODELS[model], dev(maps), tab, ne, 180.0)
+    assert_close(host(out), host(ref), TOL, "signal")
+    gm = ops.ideal_bwd(MODELS[model], dev(maps), tab, ne, dev(up), 180.0)
+    assert_close(host(gm), host(gref), TOL, "grad maps")
+
+
+def test_analytic_known_answers():
+    """SURVEY §8c KAT (i)/(ii): pure water, no decay: S_e = 1.4 W exp(2 pi i te phi)."""
+    nb, H, W, ne = 1, 8, 8, 6
+    maps = np.zeros((nb, 3, H, W, 2), np.float32)
+    maps[:, 0, :, :, 0] = 0.5
+    te = synth.te_orig(nb, ne)
+    tab = ops.gen_tables(dev(te), 1.5)
+    out = host(ops.ideal_fwd(L.MODEL_WFPM, dev(maps), tab, ne))
+    assert np.abs(out[..., 0] - np.float32(0.5) * np.float32(1.4)).max() < 2e-7 and np.abs(out[..., 1]).max() < 2e-7
+    maps[:, 2, :, :, 0] = 0.1
+    out = host(ops.ideal_fwd(L.MODEL_WFPM, dev(maps), tab, ne))
+    ph = 2 * np.pi * te[0, :, 0].astype(np.float64) * 30.0
+    assert np.abs(out[0, :, 0, 0, 0] - 0.7 * np.cos(ph)).max() < 5e-7
+    assert np.abs(out[0, :, 0, 0, 1] - 0.7 * np.sin(ph)).max() < 5e-7
+
+
+@pytest.mark.parametrize("prefix,model,field", [("c4", "magpha", 1.5), ("wl", "wfpm", 3.0)])
+def test_fused_forward_loss_vs_reference_vectors(golden, prefix, model, field):
+    g = golden("losses")
+    tab = ops.gen_tables(dev(g[prefix + "_te"]), field)
+    loss, gm, shat = ops.ideal_loss(MODELS[model], dev(g[prefix + "_maps"]), dev(g[prefix + "_acqs"]), tab, want_shat=True)
+    assert abs(loss.item() - float(g[prefix + "_loss"])) <= TOL * float(g[prefix + "_loss"])
+    assert_close(host(gm), g[prefix + "_gmaps"], TOL, "grad maps")
+    ref = {"magpha": orc.IDEAL_mag_phase, "wfpm": orc.IDEAL_model}[model](cpu(g[prefix + "_maps"]), [field, cpu(g[prefix + "_te"])])
+    assert_close(host(shat), host(ref), TOL, "S_hat")
+
+
+@pytest.mark.parametrize("model", ["wfpm", "ffpd", "magpha"])
+@pytest.mark.parametrize("hw", [(7, 9), (40, 40)])
+def test_fused_forward_loss_vs_oracle(model, hw):
+    rng = np.random.default_rng(7)
+    H, W = hw
+    nb, ne = 2, 6
+    gen = {"wfpm": lambda: synth.wfpm_maps(nb, H, W, rng, bipolar=True), "ffpd": lambda: synth.ffpd_maps(nb, H, W, rng),
+           "magpha": lambda: synth.magpha_maps(nb, H, W, rng)}[model]
+    maps = gen()
+    te = synth.te_random(nb, ne, rng)
+    fn = {"wfpm": orc.IDEAL_model, "ffpd": orc.IDEAL_mag, "magpha": orc.IDEAL_mag_phase}[model]
+    acqs = synth.add_noise(host(fn(cpu(maps), [1.5, cpu(te)])), rng)
+    acqs[0, 1, H // 2, W // 2, 0] = 0.0                      # a single zeroed component inside the object
+    est = maps + 0.02 * rng.standard_normal(maps.shape).astype(np.float32) * (maps != 0)
+    m = cpu(est, grad=True)
+    lref, _ = orc.physics_loss_fwd(cpu(acqs), m, cpu(te), model=model)
+    (gref,) = torch.autograd.grad(lref, [m])
+    tab = ops.gen_tables(dev(te), 1.5)
+    loss, gm, _ = ops.ideal_loss(MODELS[model], dev(est), dev(acqs), tab)
+    assert abs(loss.item() - lref.item()) <= TOL * lref.item()
+    assert_close(host(gm), host(gref), TOL, "grad maps")
+
+
+@pytest.mark.parametrize("name", ["rho_orig6", "rho_rand6_pc", "rho_rand9"])
+def test_get_rho_vs_reference_vectors(golden, name):
+    g = golden("solve")
+    pc = bool(g[name + "_pc"])
+    flags = L.F_PHASE_CONSTRAINT if pc else 0
+    r2 = float(g[name + "_r2sc"])
+    tab = ops.gen_tables(dev(g[name + "_te"]), float(g[name + "_field"]))
+    a, p = dev(g[name + "_acqs"]), dev(g[name + "_pm"])
+    rho, dem = ops.get_rho_fwd(a, p, tab, r2, flags, want_demod=True)
+    assert_close(host(rho), g[name + "_rho"], TOL, "rho")
+    assert_close(host(dem), g[name + "_demod"], TOL, "demod")
+    if not pc:
+        ga, gp = ops.get_rho_bwd(a, p, tab, dev(g[name + "_up_rho"]), dev(g[name + "_up_demod"]), r2)
+        assert_close(host(ga), g[name + "_gacqs"], TOL, "grad acqs")
+        assert_close(host(gp), g[name + "_gpm"], TOL, "grad pm")
+
+
+def test_get_rho_bipolar_and_flat_vs_reference_vectors(golden):
+    g = golden("solve")
+    tab = ops.gen_tables(dev(g["rho_bip_te"]), 1.5)
+    a, p = dev(g["rho_bip_acqs"]), dev(g["rho_bip_pm"])
+    rho, _ = ops.get_rho_fwd(a, p, tab)
+    assert_close(host(rho), g["rho_bip_rho"], TOL)
+    ga, gp = ops.get_rho_bwd(a, p, tab, dev(g["rho_bip_up_rho"]), None)
+    assert_close(host(ga), g["rho_bip_gacqs"], TOL)
+    assert_close(host(gp), g["rho_bip_gpm"], TOL)
+    nb = g["rho_flat_acqs"].shape[0]
+    tab = ops.gen_tables(dev(synth.te_orig(nb, 6)), 1.5)
+    a, p = dev(g["rho_flat_acqs"]), dev(g["rho_flat_pm"])
+    rho, _ = ops.get_rho_fwd(a, p, tab, flags=L.F_FLAT)
+    assert_close(host(rho), g["rho_flat_rho"], TOL)
+    ga, gp = ops.get_rho_bwd(a, p, tab, dev(g["rho_flat_up_rho"]), None, flags=L.F_FLAT)
+    assert_close(host(ga), g["rho_flat_gacqs"], TOL)
+    assert_close(host(gp), g["rho_flat_gpm"], TOL)
+
+
+@pytest.mark.parametrize("name", ["a2a_orig6", "a2a_3T", "a2a_rand7"])
+def test_acq_to_acq_and_config2_loss_vs_reference_vectors(golden, name):
+    g = golden("solve")
+    tab = ops.gen_tables(dev(g[name + "_te"]), float(g[name + "_field"]))
+    a, p = dev(g[name + "_acqs"]), dev(g[name + "_pm"])
+    rho, shat = ops.a2a_fwd(a, p, tab)
+    assert_close(host(shat), g[name + "_out"], TOL, "S_hat")
+    ga, gp = ops.a2a_bwd(a, p, tab, None, dev(g[name + "_up"]))
+    assert_close(host(ga), g[name + "_gacqs"], TOL, "grad acqs")
+    assert_close(host(gp), g[name + "_gpm"], TOL, "grad pm")
+    loss, gl, rho2, shat2 = ops.a2a_loss(a, p, tab, want_rho=True, want_shat=True)
+    assert abs(loss.item() - float(g[name + "_loss"])) <= TOL * float(g[name + "_loss"])
+    assert_close(host(gl), g[name + "_loss_gpm"], TOL, "loss grad pm")
+    assert_close(host(shat2), g[name + "_out"], TOL)
+    assert_close(host(rho2), host(rho), 1e-6)
+    loss_b, gl_b, _, _ = ops.a2a_loss(a, p, tab)
+    assert loss_b.item() == loss.item() and torch.equal(gl_b, gl)
+
+
+@pytest.mark.parametrize("hw", [(9, 7), (48, 64)])
+@pytest.mark.parametrize("ne", [2, 5, 6, 12])
+def test_acq_to_acq_family_vs_oracle(hw, ne):
+    rng = np.random.default_rng(31 + ne)
+    H, W = hw
+    nb = 2
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+    te = synth.te_random(nb, ne, rng, d_te_min=0.9e-3 if ne > 8 else 1.6e-3, d_te_d=0.3e-3 if ne > 8 else 1.0e-3)
+    acqs = synth.add_noise(host(orc.IDEAL_model(cpu(maps), [1.5, cpu(te)])), rng)
+    pm = maps[:, 2:3] + 0.03 * rng.standard_normal(maps[:, 2:3].shape).astype(np.float32) * (maps[:, 2:3] != 0)
+    a, p = cpu(acqs, True), cpu(pm, True)
+    for only_mag in (False, True):
+        rho_r, s_r = orc.acq_to_acq(a, p, te=cpu(te), only_mag=only_mag)
+        up_r, up_s = rng.standard_normal(rho_r.shape).astype(np.float32), rng.standard_normal(s_r.shape).astype(np.float32)
+        ga_r, gp_r = torch.autograd.grad((rho_r * cpu(up_r)).sum() + (s_r * cpu(up_s)).sum(), [a, p])
+        tab = ops.gen_tables(dev(te), 1.5)
+        flags = L.F_ONLY_MAG if only_mag else 0
+        rho, shat = ops.a2a_fwd(dev(acqs), dev(pm), tab, flags=flags)
+        assert_close(host(rho), host(rho_r), TOL, "rho")
+        assert_close(host(shat), host(s_r), TOL, "S_hat")
+        ga, gp = ops.a2a_bwd(dev(acqs), dev(pm), tab, dev(up_r), dev(up_s), flags=flags)
+        assert_close(host(ga), host(ga_r), TOL, "grad acqs")
+        assert_close(host(gp), host(gp_r), TOL, "grad pm")
+    # fused objective, including the per-component mask (ragged voxels -> slow path)
+    acqs2 = acqs.copy()
+    acqs2[0, 0, H // 2, W // 2, 1] = 0.0
+    acqs2[1, ne - 1, H // 2, 1:4, :] = 0.0
+    p2 = cpu(pm, True)
+    lref, _, _ = orc.physics_loss_a2a(cpu(acqs2), p2, te=cpu(te))
+    (gref,) = torch.autograd.grad(lref, [p2])
+    loss, gl, _, _ = ops.a2a_loss(dev(acqs2), dev(pm), tab)
+    assert abs(loss.item() - lref.item()) <= TOL * lref.item()
+    assert_close(host(gl), host(gref), TOL, "loss grad pm")
+
+
+def test_full_size_properties():
+    """BASELINE-size slices (384 x 384 x 6): size-independent properties instead of an oracle run."""
+    rng = np.random.default_rng(1234)
+    nb, H, W, ne = 4, 384, 384, 6
+    maps = dev(synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0))
+    te = dev(synth.te_random(nb, ne, rng))
+    tab = ops.gen_tables(te, 1.5)
+    S = ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne)
+    rho, _ = ops.get_rho_fwd(S, maps[:, 2:3].contiguous(), tab)                      # encode -> solve round trip
+    assert_close(host(rho), host(maps[:, :2]), 3e-6, "round trip")
+    rho2, S2 = ops.a2a_fwd(S, maps[:, 2:3].contiguous(), tab)                        # model signals are a fixed point
+    assert_close(host(S2), host(S), 3e-6, "fixed point")
+    noisy = S + 0.02 * torch.randn_like(S) * (S != 0)
+    _, P1 = ops.a2a_fwd(noisy, maps[:, 2:3].contiguous(), tab)
+    _, P2 = ops.a2a_fwd(P1, maps[:, 2:3].contiguous(), tab)                          # projector idempotence
+    assert_close(host(P2), host(P1), 3e-6, "idempotence")
+    pm = maps[:, 2:3].contiguous()
+    loss0, g0, _, _ = ops.a2a_loss(S, pm, tab)                                       # noiseless data: zero objective
+    assert loss0.item() < 1e-12 and g0.abs().max().item() < 1e-7
+    loss, gl, _, shat = ops.a2a_loss(noisy, pm, tab, want_shat=True)                 # fused == unfused composition
+    masked = torch.where(noisy != 0, shat, torch.zeros_like(shat))
+    ref_loss = ((masked - noisy).double() ** 2).mean().item()
+    assert abs(loss.item() - ref_loss) <= 2e-6 * ref_loss
+    up = 2.0 * (masked - noisy) / noisy.numel()
+    _, gp = ops.a2a_bwd(noisy, pm, tab, None, up.contiguous(), need_acqs=False)
+    assert_close(host(gl), host(gp), 2e-5, "fused vs unfused gradient")
+    lin = ops.ideal_fwd(L.MODEL_WFPM, torch.cat([2.0 * maps[:, :2], maps[:, 2:]], 1).contiguous(), tab, ne)   # linear in rho
+    assert_close(host(lin), host(2.0 * S), 1e-6, "linearity")
+
+
+def test_host_pipeline_matches_device_call():
+    rng = np.random.default_rng(5)
+    nb, H, W, ne = 7, 32, 32, 6
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+    te = synth.te_random(nb, ne, rng)
+    acqs = synth.add_noise(host(orc.IDEAL_model(cpu(maps), [1.5, cpu(te)])), rng)
+    pm = np.ascontiguousarray(maps[:, 2:3])
+    tab = ops.gen_tables(dev(te), 1.5)
+    loss, g, _, _ = ops.a2a_loss(dev(acqs), dev(pm), tab)
+    lib = L.load()
+    ctx = ctypes.c_void_p()
+    L.check(lib.ig_ctx_create(0, 3, ne, H * W, ctypes.byref(ctx)), "ctx")
+    try:
+        a_h, p_h, t_h = (torch.from_numpy(x).pin_memory() for x in (acqs, pm, np.ascontiguousarray(te[:, :, 0])))
+        g_h = torch.empty(nb, 1, H, W, 2).pin_memory()
+        l_h = torch.empty(1).pin_memory()
+        L.check(lib.ig_a2a_loss_host(ctx, a_h.data_ptr(), p_h.data_ptr(), t_h.data_ptr(), nb, 1.5, 200.0, 1.0 / acqs.size,
+                                     l_h.data_ptr(), g_h.data_ptr()), "host pipeline")
+    finally:
+        lib.ig_ctx_destroy(ctx)
+    assert abs(l_h.item() - loss.item()) <= 1e-6 * loss.item()
+    assert torch.equal(g_h, g.cpu())
