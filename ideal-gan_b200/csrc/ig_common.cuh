@@ -137,8 +137,13 @@ __device__ __forceinline__ void unit_phasor(float turns, float &c, float &s) {
     s = __sinf(r);
 }
 __device__ __forceinline__ void unit_phasor(pk turns, pk &c, pk &s) {
-    unit_phasor(turns.d.x, c.d.x, s.d.x);
-    unit_phasor(turns.d.y, c.d.y, s.d.y);
+    // same reduction, packed: 3 FADD2 + 1 FMUL2 for the two voxels, then the SFU per lane
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    float2 n = __fadd2_rn(turns.d, magic);
+    n = __fadd2_rn(n, nmagic);
+    const float2 r = __fmul2_rn(__ffma2_rn(n, make_float2(-1.f, -1.f), turns.d), make_float2(kTwoPi, kTwoPi));
+    c = mk(__cosf(r.x), __cosf(r.y));
+    s = mk(__sinf(r.x), __sinf(r.y));
 }
 __device__ __forceinline__ pk fast_ex2(pk x) { return mk(fast_ex2(x.d.x), fast_ex2(x.d.y)); }
 __device__ __forceinline__ float vrelu(float x) { return fmaxf(x, 0.f); }
@@ -189,33 +194,29 @@ __device__ __forceinline__ void lane_set(pk &x, int l, float v) { if (l) x.d.y =
 // ------------------------------------------------------------------------------------------------
 // per-sample table staged in shared memory
 // ------------------------------------------------------------------------------------------------
+struct __align__(16) EchoRec {
+    float te;      // seconds
+    float kphi;    // te * fm_sc            : turns per unit of the phi/300 map
+    float kdec;    // -te * r2_sc * log2(e) : log2 of the decay per unit of the R2*/r2_sc map (global table: -te log2 e)
+    float sgn;     // (-1)^e, e = 1..ne     : bipolar odd/even sign
+    float c_re, c_im;
+    float pw_re, pw_im, pf_re, pf_im;
+    float tpw_re, tpw_im, tpf_re, tpf_im;   // te * M^+ rows
+    float pad0, pad1;
+};
+static_assert(sizeof(EchoRec) == IG_REC_FLOATS * sizeof(float), "echo record layout");
+
 template <int NE> struct SampleTab {
-    float te[NE];     // seconds
-    float kphi[NE];   // te * fm_sc            : turns per unit of the phi/300 map
-    float kdec[NE];   // -te * r2_sc * log2(e) : log2 of the decay per unit of the R2*/r2_sc map
-    float sgn[NE];    // (-1)^e, e = 1..ne     : bipolar odd/even sign
-    float c_re[NE], c_im[NE];
-    float pw_re[NE], pw_im[NE], pf_re[NE], pf_im[NE];
-    float ap0[NE], ap1[NE], ap2[NE];
+    EchoRec r[NE];
 };
 
+// Straight 16-byte copy of the sample's first NE echo records (records beyond `ne` are zero in the global
+// table); the one r2_sc-dependent field is scaled on the way.  Only NE*4 threads take part.
 template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, const float *__restrict__ tab_b, int ne, float r2_sc) {
-    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
-        const bool live = e < ne;
-        const float te = live ? tab_b[IG_ROW_TE * IG_MAX_NE + e] : 0.f;
-        t.te[e] = te;
-        t.kphi[e] = te * kFmSc;
-        t.kdec[e] = -te * r2_sc * kLog2e;
-        t.sgn[e] = (e & 1) ? 1.f : -1.f;
-        t.c_re[e] = live ? tab_b[IG_ROW_C_RE * IG_MAX_NE + e] : 0.f;
-        t.c_im[e] = live ? tab_b[IG_ROW_C_IM * IG_MAX_NE + e] : 0.f;
-        t.pw_re[e] = live ? tab_b[IG_ROW_PW_RE * IG_MAX_NE + e] : 0.f;
-        t.pw_im[e] = live ? tab_b[IG_ROW_PW_IM * IG_MAX_NE + e] : 0.f;
-        t.pf_re[e] = live ? tab_b[IG_ROW_PF_RE * IG_MAX_NE + e] : 0.f;
-        t.pf_im[e] = live ? tab_b[IG_ROW_PF_IM * IG_MAX_NE + e] : 0.f;
-        t.ap0[e] = live ? tab_b[IG_ROW_AP0 * IG_MAX_NE + e] : 0.f;
-        t.ap1[e] = live ? tab_b[IG_ROW_AP1 * IG_MAX_NE + e] : 0.f;
-        t.ap2[e] = live ? tab_b[IG_ROW_AP2 * IG_MAX_NE + e] : 0.f;
+    if (threadIdx.x < NE * 4) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(tab_b) + threadIdx.x);
+        if ((threadIdx.x & 3) == 0) v.z *= r2_sc;
+        reinterpret_cast<float4 *>(t.r)[threadIdx.x] = v;
     }
     __syncthreads();
 }

@@ -182,10 +182,10 @@ __global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
                 V c, s;
-                unit_phasor(vfma(T.sgn[e], x.bturn, vmul(T.kphi[e], x.phi_t)), c, s);
-                const V d = fast_ex2(vmul(T.kdec[e], x.r2));
+                unit_phasor(vfma(T.r[e].sgn, x.bturn, vmul(T.r[e].kphi, x.phi_t)), c, s);
+                const V d = fast_ex2(vmul(T.r[e].kdec, x.r2));
                 const cx<V> w{vmul(d, c), vmul(d, s)};
-                const cx<V> yhat = caffine(x.rhoW, T.c_re[e], T.c_im[e], x.rhoF);
+                const cx<V> yhat = caffine(x.rhoW, T.r[e].c_re, T.r[e].c_im, x.rhoF);
                 const cx<V> shat = cmulv(w, yhat);
                 if constexpr (MODE == MODE_FWD) {
                     st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
@@ -202,12 +202,12 @@ __global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
                     const cx<V> g = cmulc(w, G);
                     a.sg.re = vadd(a.sg.re, g.re);
                     a.sg.im = vadd(a.sg.im, g.im);
-                    cmac(a.sgc, T.c_re[e], -T.c_im[e], g);
+                    cmac(a.sgc, T.r[e].c_re, -T.r[e].c_im, g);
                     const cx<V> q = cmulc(g, yhat);
-                    a.tq.re = vfma(T.te[e], q.re, a.tq.re);
-                    a.tq.im = vfma(T.te[e], q.im, a.tq.im);
+                    a.tq.re = vfma(T.r[e].te, q.re, a.tq.re);
+                    a.tq.im = vfma(T.r[e].te, q.im, a.tq.im);
                     if constexpr (MODEL == IG_MODEL_FFPD) { a.q.re = vadd(a.q.re, q.re); a.q.im = vadd(a.q.im, q.im); }
-                    if constexpr (MODEL != IG_MODEL_FFPD) a.bq = vfma(T.sgn[e], q.im, a.bq);
+                    if constexpr (MODEL != IG_MODEL_FFPD) a.bq = vfma(T.r[e].sgn, q.im, a.bq);
                 }
             }
         }

@@ -7,6 +7,8 @@
 //     rho = M^+ y          yhat = M rho          S_hat_e = Wp_e yhat_e         (Wp_e = 1 / Wm_e)
 // The pseudo-inverse M^+ depends only on the sample's echo times, so it is a shared-memory table and the
 // "solve" is a 2 x ne complex contraction held in registers.
+#include <stdlib.h>
+
 #include "ig_common.cuh"
 
 namespace ig {
@@ -60,8 +62,16 @@ template <typename V> struct Mod {
 };
 template <int NE, typename V> __device__ __forceinline__ Mod<V> modulator(const SampleTab<NE> &T, int e, V phi_t, V r2, V bturn) {
     Mod<V> m;
-    unit_phasor(vfma(T.sgn[e], bturn, vmul(T.kphi[e], phi_t)), m.c, m.s);
-    const V lg = vmul(T.kdec[e], r2);
+    unit_phasor(vfma(T.r[e].sgn, bturn, vmul(T.r[e].kphi, phi_t)), m.c, m.s);
+    const V lg = vmul(T.r[e].kdec, r2);
+    m.d = fast_ex2(lg);
+    m.dinv = fast_ex2(vneg(lg));
+    return m;
+}
+template <typename V> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
+    Mod<V> m;
+    unit_phasor(vfma(R.sgn, bturn, vmul(R.kphi, phi_t)), m.c, m.s);
+    const V lg = vmul(R.kdec, r2);
     m.d = fast_ex2(lg);
     m.dinv = fast_ex2(vneg(lg));
     return m;
@@ -114,8 +124,8 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
             const Mod<V> m = modulator(T, e, phi_t, r2, bturn);
             const cx<V> y = demod(m, S[e]);
             if (p.demod) st_cx(p.demod + acq_b + static_cast<size_t>(e) * nv * 2, v0, y);
-            cmac(rw, T.pw_re[e], T.pw_im[e], y);
-            cmac(rf, T.pf_re[e], T.pf_im[e], y);
+            cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y);
+            cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y);
         }
     }
     if (p.flags & IG_F_PHASE_CONSTRAINT) {
@@ -191,8 +201,8 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
             const Mod<V> m = modulator(T, e, phi_t, r2, bturn);
             const cx<V> y = demod(m, S[e]);
             cx<V> gy = czero<V>();
-            cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
-            cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+            cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
+            cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
             if (p.g_demod) {
                 const cx<V> gd = ld_cx(p.g_demod + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
                 gy.re = vadd(gy.re, gd.re);
@@ -200,9 +210,9 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
             }
             if (p.g_acqs) st_echo<V, FLAT>(p.g_acqs + acq_b, e, ne, nv, v0, remod_inv(m, gy));
             const cx<V> q = cmulc(gy, y);
-            X.re = vfma(T.te[e], q.re, X.re);
-            X.im = vfma(T.te[e], q.im, X.im);
-            B = vfma(T.sgn[e], q.im, B);
+            X.re = vfma(T.r[e].te, q.re, X.re);
+            X.im = vfma(T.r[e].te, q.im, X.im);
+            B = vfma(T.r[e].sgn, q.im, B);
         }
     }
     const V gphi = vmul(kTwoPi * kFmSc, X.im), gr2 = vmul(p.r2_sc, X.re);
@@ -236,8 +246,8 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_fw
         if (e < ne) {
             m[e] = modulator(T, e, phi_t, r2, zero);
             const cx<V> y = demod(m[e], S[e]);
-            cmac(rw, T.pw_re[e], T.pw_im[e], y);
-            cmac(rf, T.pf_re[e], T.pf_im[e], y);
+            cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y);
+            cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y);
         }
     }
     if (p.rho) {
@@ -249,7 +259,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_fw
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
-            const cx<V> sh = remod(m[e], caffine(rw, T.c_re[e], T.c_im[e], rf));
+            const cx<V> sh = remod(m[e], caffine(rw, T.r[e].c_re, T.r[e].c_im, rf));
             if (p.flags & IG_F_ONLY_MAG) {
                 st_real(p.shat + static_cast<size_t>(b) * ne * nv + static_cast<size_t>(e) * nv, v0, vsqrt(vfma(sh.re, sh.re, vmul(sh.im, sh.im))));
             } else {
@@ -283,8 +293,8 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
         if (e < ne) {
             m[e] = modulator(T, e, phi_t, r2, zero);
             y[e] = demod(m[e], ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{}));
-            cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
-            cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
+            cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y[e]);
+            cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y[e]);
         }
     }
     // pass over the upstream of S_hat: v_e, M^H v, and the -conj(v) yhat part of X
@@ -293,7 +303,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
-                const cx<V> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
+                const cx<V> yhat = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
                 cx<V> G;
                 if (p.flags & IG_F_ONLY_MAG) {
                     // |S_hat| = d |yhat| ; G = g S_hat / |S_hat| ; v = conj(Wp) G = g d yhat / |yhat|  (0 where |yhat| = 0)
@@ -311,10 +321,10 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
                 const cx<V> v = G;
                 gw.re = vadd(gw.re, v.re);
                 gw.im = vadd(gw.im, v.im);
-                cmac(gf, T.c_re[e], -T.c_im[e], v);
+                cmac(gf, T.r[e].c_re, -T.r[e].c_im, v);
                 const cx<V> q = cmulc(v, yhat);
-                X.re = vfma(-T.te[e], q.re, X.re);
-                X.im = vfma(-T.te[e], q.im, X.im);
+                X.re = vfma(-T.r[e].te, q.re, X.re);
+                X.im = vfma(-T.r[e].te, q.im, X.im);
             }
         }
     }
@@ -329,12 +339,12 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
             cx<V> gy = czero<V>();
-            cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
-            cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+            cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
+            cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
             if (p.g_acqs) st_cx(p.g_acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod_inv(m[e], gy));
             const cx<V> q = cmulc(gy, y[e]);
-            X.re = vfma(T.te[e], q.re, X.re);
-            X.im = vfma(T.te[e], q.im, X.im);
+            X.re = vfma(T.r[e].te, q.re, X.re);
+            X.im = vfma(T.r[e].te, q.im, X.im);
         }
     }
     st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(kTwoPi * kFmSc, X.im), vmul(p.r2_sc, X.re)});
@@ -352,96 +362,142 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
 // component exactly as the reference does (train-IDEAL-unsup.py:218) with the general adjoint.
 // =================================================================================================
 template <int NE>
-__device__ __noinline__ void a2a_loss_slow_voxel(const SampleTab<NE> &T, const float *acq_b, int ne, int nv, int v, float phi_t, float r2,
+__device__ __forceinline__ void a2a_loss_slow_voxel(const SampleTab<NE> &T, const float *acq_b, int ne, int nv, int v, float phi_t, float r2,
                                                  float r2_sc, float &loss, float &gphi, float &gr2) {
     cx<float> y[NE], vv[NE];
     Mod<float> m[NE];
     cx<float> rw = czero<float>(), rf = czero<float>();
+#pragma unroll 1
     for (int e = 0; e < ne; ++e) {
         m[e] = modulator(T, e, phi_t, r2, 0.f);
         const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
         y[e] = demod(m[e], cx<float>{s.x, s.y});
-        cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
-        cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
+        cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y[e]);
+        cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y[e]);
     }
     cx<float> gw = czero<float>(), gf = czero<float>(), X = czero<float>();
     loss = 0.f;
+#pragma unroll 1
     for (int e = 0; e < ne; ++e) {
         const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
-        const cx<float> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
+        const cx<float> yhat = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
         const cx<float> sh = remod(m[e], yhat);
         const cx<float> E{mask_sub(sh.re, s.x), mask_sub(sh.im, s.y)};
         loss += E.re * E.re + E.im * E.im;
         vv[e] = demod_fwd(m[e], E);
         gw.re += vv[e].re;
         gw.im += vv[e].im;
-        cmac(gf, T.c_re[e], -T.c_im[e], vv[e]);
+        cmac(gf, T.r[e].c_re, -T.r[e].c_im, vv[e]);
         const cx<float> q = cmulc(vv[e], yhat);
-        X.re = fmaf(-T.te[e], q.re, X.re);
-        X.im = fmaf(-T.te[e], q.im, X.im);
+        X.re = fmaf(-T.r[e].te, q.re, X.re);
+        X.im = fmaf(-T.r[e].te, q.im, X.im);
     }
+#pragma unroll 1
     for (int e = 0; e < ne; ++e) {
         cx<float> gy = czero<float>();
-        cmac(gy, T.pw_re[e], -T.pw_im[e], gw);
-        cmac(gy, T.pf_re[e], -T.pf_im[e], gf);
+        cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
+        cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
         const cx<float> q = cmulc(gy, y[e]);
-        X.re = fmaf(T.te[e], q.re, X.re);
-        X.im = fmaf(T.te[e], q.im, X.im);
+        X.re = fmaf(T.r[e].te, q.re, X.re);
+        X.im = fmaf(T.r[e].te, q.im, X.im);
     }
     gphi = kTwoPi * kFmSc * X.im;      // caller applies 2 / N
     gr2 = r2_sc * X.re;
 }
 
-template <int NE, typename V, bool OUTPUTS> __global__ void __launch_bounds__(kThreads) a2a_loss_kernel(const SolveParams p) {
+// raw echoes of the thread's voxels exactly as loaded (one 8- or 16-byte access per echo)
+template <typename V> struct RawEcho;
+template <> struct RawEcho<float> { float2 v; };
+template <> struct RawEcho<pk> { float4 v; };
+__device__ __forceinline__ RawEcho<float> ld_raw(const float *plane, int v0, float) {
+    RawEcho<float> r; r.v = __ldcs(reinterpret_cast<const float2 *>(plane) + v0); return r;
+}
+__device__ __forceinline__ RawEcho<pk> ld_raw(const float *plane, int v0, pk) {
+    RawEcho<pk> r; r.v = __ldcs(reinterpret_cast<const float4 *>(plane) + (v0 >> 1)); return r;
+}
+// running min / max of |component| per voxel: a voxel is "ragged" (needs the per-component mask) iff
+// min == 0 < max.  FMNMX runs on the ALU pipe, which this kernel otherwise leaves idle.
+struct AbsRange { float lo0, hi0, lo1, hi1; };
+__device__ __forceinline__ void abs_range(AbsRange &a, const RawEcho<float> &r) {
+    a.lo0 = fminf(fminf(a.lo0, fabsf(r.v.x)), fabsf(r.v.y));
+    a.hi0 = fmaxf(fmaxf(a.hi0, fabsf(r.v.x)), fabsf(r.v.y));
+}
+__device__ __forceinline__ void abs_range(AbsRange &a, const RawEcho<pk> &r) {
+    a.lo0 = fminf(fminf(a.lo0, fabsf(r.v.x)), fabsf(r.v.y));
+    a.hi0 = fmaxf(fmaxf(a.hi0, fabsf(r.v.x)), fabsf(r.v.y));
+    a.lo1 = fminf(fminf(a.lo1, fabsf(r.v.z)), fabsf(r.v.w));
+    a.hi1 = fmaxf(fmaxf(a.hi1, fabsf(r.v.z)), fabsf(r.v.w));
+}
+__device__ __forceinline__ bool is_ragged(const AbsRange &a) { return (a.lo0 == 0.f && a.hi0 > 0.f) || (a.lo1 == 0.f && a.hi1 > 0.f); }
+__device__ __forceinline__ cx<float> raw_cx(const RawEcho<float> &r) { return cx<float>{r.v.x, r.v.y}; }
+__device__ __forceinline__ cx<pk> raw_cx(const RawEcho<pk> &r) { return cx<pk>{mk(r.v.x, r.v.z), mk(r.v.y, r.v.w)}; }
+// y = (cd - i sd) * S, written lane by lane with scalar FMAs straight from the loaded (re, im, re, im) tuple:
+// this de-interleaves into the packed layout for free instead of paying register moves before FFMA2.
+__device__ __forceinline__ cx<float> demod_raw(float cd, float sd, const RawEcho<float> &r) {
+    return cx<float>{fmaf(sd, r.v.y, cd * r.v.x), fmaf(-sd, r.v.x, cd * r.v.y)};
+}
+__device__ __forceinline__ cx<pk> demod_raw(pk cd, pk sd, const RawEcho<pk> &r) {
+    cx<pk> y;
+    y.re = mk(fmaf(sd.d.x, r.v.y, cd.d.x * r.v.x), fmaf(sd.d.y, r.v.w, cd.d.y * r.v.z));
+    y.im = mk(fmaf(-sd.d.x, r.v.x, cd.d.x * r.v.y), fmaf(-sd.d.y, r.v.z, cd.d.y * r.v.w));
+    return y;
+}
+
+// Persistent grid: each block owns a contiguous range of (sample, tile) work items, restaging the table only
+// when it crosses into the next sample, and takes part in the loss reduction once at the very end.
+template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_bounds__(kThreads, MINB) a2a_loss_kernel(const SolveParams p) {
     __shared__ SampleTab<NE> T;
-    __shared__ float tpw_re[NE], tpw_im[NE], tpf_re[NE], tpf_im[NE];   // te * M^+ rows
-    const int b = blockIdx.y;
-    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
-    if (threadIdx.x < NE) {
-        const int e = threadIdx.x;
-        tpw_re[e] = T.te[e] * T.pw_re[e]; tpw_im[e] = T.te[e] * T.pw_im[e];
-        tpf_re[e] = T.te[e] * T.pf_re[e]; tpf_im[e] = T.te[e] * T.pf_im[e];
-    }
-    __syncthreads();
-    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
-    const bool active = v0 < p.nv;
     const int nv = p.nv, ne = p.ne;
-    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    const int tiles_ps = (nv + kThreads * lanes<V>::n - 1) / (kThreads * lanes<V>::n);
+    const long total = static_cast<long>(p.nb) * tiles_ps;
+    const int tile_end = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
+    int cur_b = -1;
     float loss_part = 0.f;
+    for (int tile = static_cast<int>(total * blockIdx.x / gridDim.x); tile < tile_end; ++tile) {
+    const int b = tile / tiles_ps;
+    if (b != cur_b) {
+        if (cur_b >= 0) __syncthreads();          // everyone is done reading the previous sample's table
+        stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, ne, p.r2_sc);
+        cur_b = b;
+    }
+    const int v0 = ((tile - b * tiles_ps) * kThreads + threadIdx.x) * lanes<V>::n;
+    const bool active = v0 < nv;
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
     bool ragged = false;      // a voxel with some, but not all, components exactly zero
-    cx<V> y[NE];
+    RawEcho<V> raw[NE];
     V phi_t = splat<V>(0.f), r2 = splat<V>(0.f);
     if (active) {
+        const float *plane = p.acqs + acq_b;
+        const size_t plane_stride = static_cast<size_t>(nv) * 2;
 #pragma unroll
         for (int e = 0; e < NE; ++e)
-            if (e < ne) y[e] = ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{});
+            if (e < ne) raw[e] = ld_raw(plane + e * plane_stride, v0, V{});
         ld_pm<V, false>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
+        AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
 #pragma unroll
-        for (int l = 0; l < lanes<V>::n; ++l) {
-            int nz = 0;
-#pragma unroll
-            for (int e = 0; e < NE; ++e)
-                if (e < ne) nz += (lane_get(y[e].re, l) != 0.f) + (lane_get(y[e].im, l) != 0.f);
-            ragged |= (nz != 0 && nz != 2 * ne);
-        }
+        for (int e = 0; e < NE; ++e)
+            if (e < ne) abs_range(ar, raw[e]);
+        ragged = is_ragged(ar);
     }
     const bool warp_ragged = __any_sync(0xffffffffu, ragged);
     if (active && !warp_ragged) {
         const V zero = splat<V>(0.f);
         V d2[NE];
+        cx<V> y[NE];
         cx<V> rw = czero<V>(), rf = czero<V>(), tw = czero<V>(), tf = czero<V>();
         [[maybe_unused]] Mod<V> mods[OUTPUTS ? NE : 1];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
-                const Mod<V> m = modulator(T, e, phi_t, r2, zero);
+                const EchoRec R = T.r[e];
+                const Mod<V> m = modulator_rec(R, phi_t, r2, zero);
                 if constexpr (OUTPUTS) mods[e] = m;
                 d2[e] = vmul(m.d, m.d);
-                y[e] = demod(m, y[e]);
-                cmac(rw, T.pw_re[e], T.pw_im[e], y[e]);
-                cmac(rf, T.pf_re[e], T.pf_im[e], y[e]);
-                cmac(tw, tpw_re[e], tpw_im[e], y[e]);
-                cmac(tf, tpf_re[e], tpf_im[e], y[e]);
+                y[e] = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw[e]);
+                cmac(rw, R.pw_re, R.pw_im, y[e]);
+                cmac(rf, R.pf_re, R.pf_im, y[e]);
+                cmac(tw, R.tpw_re, R.tpw_im, y[e]);
+                cmac(tf, R.tpf_re, R.tpf_im, y[e]);
             }
         }
         V lsum = zero;
@@ -449,22 +505,24 @@ template <int NE, typename V, bool OUTPUTS> __global__ void __launch_bounds__(kT
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
-                const cx<V> yhat = caffine(rw, T.c_re[e], T.c_im[e], rf);
-                const cx<V> h = caffine(tw, T.c_re[e], T.c_im[e], tf);
+                const EchoRec R = T.r[e];
+                const cx<V> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                const cx<V> h = caffine(tw, R.c_re, R.c_im, tf);
                 const cx<V> r{vsub(yhat.re, y[e].re), vsub(yhat.im, y[e].im)};
                 const cx<V> w{vmul(d2[e], r.re), vmul(d2[e], r.im)};                      // d^2 r
                 lsum = vfma(w.re, r.re, lsum);
                 lsum = vfma(w.im, r.im, lsum);
-                const cx<V> g{vfma(T.te[e], yhat.re, vneg(h.re)), vfma(T.te[e], yhat.im, vneg(h.im))};
-                const cx<V> q = cmulc(w, g);                                              // d^2 conj(r) (te yhat - h)
-                K.re = vadd(K.re, q.re);
-                K.im = vadd(K.im, q.im);
+                const cx<V> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
+                K.re = vfma(w.re, g.re, K.re);                                            // K += conj(w) g
+                K.re = vfma(w.im, g.im, K.re);
+                K.im = vfma(w.re, g.im, K.im);
+                K.im = vfma(vneg(w.im), g.re, K.im);
                 if constexpr (OUTPUTS) {
                     if (p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod(mods[e], yhat));
                 }
             }
         }
-        loss_part = hsum(lsum);
+        loss_part += hsum(lsum);
         const cx<V> g{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * p.r2_sc * p.inv_n, K.re)};
         st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, g);
         if constexpr (OUTPUTS) {
@@ -492,14 +550,14 @@ template <int NE, typename V, bool OUTPUTS> __global__ void __launch_bounds__(kT
             for (int e = 0; e < NE; ++e) {
                 if (e < ne) {
                     mods[e] = modulator(T, e, phi_t, r2, zero);
-                    const cx<V> ye = demod(mods[e], y[e]);
-                    cmac(rw, T.pw_re[e], T.pw_im[e], ye);
-                    cmac(rf, T.pf_re[e], T.pf_im[e], ye);
+                    const cx<V> ye = demod(mods[e], raw_cx(raw[e]));
+                    cmac(rw, T.r[e].pw_re, T.r[e].pw_im, ye);
+                    cmac(rf, T.r[e].pf_re, T.r[e].pf_im, ye);
                 }
             }
 #pragma unroll
             for (int e = 0; e < NE; ++e)
-                if (e < ne && p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod(mods[e], caffine(rw, T.c_re[e], T.c_im[e], rf)));
+                if (e < ne && p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod(mods[e], caffine(rw, T.r[e].c_re, T.r[e].c_im, rf)));
             if (p.rho) {
                 const float inv = 1.0f / kRhoSc;
                 float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
@@ -508,6 +566,7 @@ template <int NE, typename V, bool OUTPUTS> __global__ void __launch_bounds__(kT
             }
         }
     }
+    }   // tile loop
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
 }
 
@@ -525,6 +584,30 @@ template <typename K1, typename K2> static int launch_pair(bool packed, const So
         kp<<<grid_for(p.nb, p.nv, 2), kThreads, 0, st>>>(p);
     } else {
         ks<<<grid_for(p.nb, p.nv, 1), kThreads, 0, st>>>(p);
+    }
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// persistent launch: one resident wave (SMs x occupancy), capped by the number of tiles
+template <typename K> static int persistent_grid(K kernel, int nb, int nv, int vpt, int *grid) {
+    int dev = 0, sms = 0, occ = 0;
+    IG_CUDA(cudaGetDevice(&dev));
+    IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0));
+    const long tiles = static_cast<long>(nb) * ((nv + kThreads * vpt - 1) / (kThreads * vpt));
+    long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
+    *grid = static_cast<int>(g < tiles ? g : tiles);
+    return 0;
+}
+template <typename K1, typename K2> static int launch_persistent(bool packed, const SolveParams &p, cudaStream_t st, K1 kp, K2 ks) {
+    int grid = 1;
+    if (packed) {
+        if (int rc = persistent_grid(kp, p.nb, p.nv, 2, &grid)) return rc;
+        kp<<<grid, kThreads, 0, st>>>(p);
+    } else {
+        if (int rc = persistent_grid(ks, p.nb, p.nv, 1, &grid)) return rc;
+        ks<<<grid, kThreads, 0, st>>>(p);
     }
     IG_CUDA(cudaGetLastError());
     return 0;
@@ -628,7 +711,9 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        if (outputs) return launch_pair(packed, p, st, a2a_loss_kernel<NE, pk, true>, a2a_loss_kernel<NE, float, true>);
-        return launch_pair(packed, p, st, a2a_loss_kernel<NE, pk, false>, a2a_loss_kernel<NE, float, false>);
+        if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
+        static const int occ3 = [] { const char *e = getenv("IG_A2A_OCC3"); return e ? atoi(e) : 0; }();     // tuning knob
+        if (occ3) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 3>, a2a_loss_kernel<NE, float, false, 3>);
+        return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
 }

@@ -2,8 +2,8 @@
 // of the magnitude design matrix.  Replaces gen_M / gen_A of the reference
 // (/root/reference/wflib/IDEAL_model.py:48-97): there, complex64 QR + triangular solve per call inside
 // the TF graph; here, closed-form normal equations in fp64 (cond(M) ~ 1.3-1.6), one
-// thread per sample, written once to a (nb, IG_TAB_FLOATS) fp32 table that every operator kernel stages
-// in shared memory.  The same code runs on the host for CPU callers (ig_gen_tables_host).
+// thread per sample, written once to a (nb, IG_TAB_FLOATS) fp32 table of per-echo records (layout in
+// include/idealgan.h) that every operator kernel stages in shared memory with 16-byte copies.  The same code runs on the host for CPU callers (ig_gen_tables_host).
 #include <math.h>
 
 #include "ig_common.cuh"
@@ -45,12 +45,16 @@ __host__ __device__ inline void build_sample_table(const float *te, int ne, floa
         s_re += re;
         s_im += im;
         q += re * re + im * im;
-        tab[IG_ROW_TE * IG_MAX_NE + e] = te[e];
-        tab[IG_ROW_C_RE * IG_MAX_NE + e] = static_cast<float>(re);
-        tab[IG_ROW_C_IM * IG_MAX_NE + e] = static_cast<float>(im);
+        float *rec = tab + e * IG_REC_FLOATS;
+        rec[IG_REC_TE] = te[e];
+        rec[IG_REC_KPHI] = te[e] * 300.0f;                                   // fm_sc (IDEAL_model.py:18)
+        rec[IG_REC_NTE_L2E] = static_cast<float>(-static_cast<double>(te[e]) * 1.4426950408889634);
+        rec[IG_REC_SGN] = (e & 1) ? 1.f : -1.f;                              // (-1)^(e+1), echoes counted from 1 (:250-251)
+        rec[IG_REC_C_RE] = static_cast<float>(re);
+        rec[IG_REC_C_IM] = static_cast<float>(im);
     }
-    tab[IG_ROW_META * IG_MAX_NE + 0] = static_cast<float>(ne);
-    tab[IG_ROW_META * IG_MAX_NE + 1] = field;
+    tab[IG_TAB_META_OFF + 0] = static_cast<float>(ne);
+    tab[IG_TAB_META_OFF + 1] = field;
     // M^H M = [[ne, s], [conj(s), q]],  M^+ = (M^H M)^-1 M^H
     const double det = static_cast<double>(ne) * q - (s_re * s_re + s_im * s_im);
     if (ne >= 2 && det > 1e-12) {
@@ -59,10 +63,18 @@ __host__ __device__ inline void build_sample_table(const float *te, int ne, floa
             // water row: (q - s conj(c_e)) / det ; fat row: (ne conj(c_e) - conj(s)) / det
             const double sc_re = s_re * cr[e] + s_im * ci[e];      // s * conj(c)
             const double sc_im = s_im * cr[e] - s_re * ci[e];
-            tab[IG_ROW_PW_RE * IG_MAX_NE + e] = static_cast<float>((q - sc_re) * inv);
-            tab[IG_ROW_PW_IM * IG_MAX_NE + e] = static_cast<float>((-sc_im) * inv);
-            tab[IG_ROW_PF_RE * IG_MAX_NE + e] = static_cast<float>((ne * cr[e] - s_re) * inv);
-            tab[IG_ROW_PF_IM * IG_MAX_NE + e] = static_cast<float>((-ne * ci[e] + s_im) * inv);
+            float *rec = tab + e * IG_REC_FLOATS;
+            const double pw_re = (q - sc_re) * inv, pw_im = (-sc_im) * inv;
+            const double pf_re = (ne * cr[e] - s_re) * inv, pf_im = (-ne * ci[e] + s_im) * inv;
+            const double t = static_cast<double>(te[e]);
+            rec[IG_REC_PW_RE] = static_cast<float>(pw_re);
+            rec[IG_REC_PW_IM] = static_cast<float>(pw_im);
+            rec[IG_REC_PF_RE] = static_cast<float>(pf_re);
+            rec[IG_REC_PF_IM] = static_cast<float>(pf_im);
+            rec[IG_REC_TPW_RE] = static_cast<float>(t * pw_re);
+            rec[IG_REC_TPW_IM] = static_cast<float>(t * pw_im);
+            rec[IG_REC_TPF_RE] = static_cast<float>(t * pf_re);
+            rec[IG_REC_TPF_IM] = static_cast<float>(t * pf_im);
         }
     }
     // A = [1, Re c, |c|^2] (gen_A, :80-90); A^+ = (A^T A)^-1 A^T by Gauss-Jordan with partial pivoting
@@ -97,7 +109,7 @@ __host__ __device__ inline void build_sample_table(const float *te, int ne, floa
                 const double a[3] = {1.0, cr[e], cr[e] * cr[e] + ci[e] * ci[e]};
                 for (int i = 0; i < 3; ++i) {
                     const double v = Ginv[i][0] * a[0] + Ginv[i][1] * a[1] + Ginv[i][2] * a[2];
-                    tab[(IG_ROW_AP0 + i) * IG_MAX_NE + e] = static_cast<float>(v);
+                    tab[IG_TAB_AP_OFF + i * IG_MAX_NE + e] = static_cast<float>(v);
                 }
             }
         }

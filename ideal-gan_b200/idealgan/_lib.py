@@ -10,9 +10,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libidealgan.so")
 
 MAX_NE = 16
-TAB_ROWS = 12
-TAB_FLOATS = TAB_ROWS * MAX_NE
-ROW_TE, ROW_C_RE, ROW_C_IM, ROW_PW_RE, ROW_PW_IM, ROW_PF_RE, ROW_PF_IM, ROW_AP0, ROW_AP1, ROW_AP2, ROW_META = range(11)
+REC_FLOATS = 16
+TAB_AP_OFF = MAX_NE * REC_FLOATS
+TAB_META_OFF = TAB_AP_OFF + 3 * MAX_NE
+TAB_FLOATS = TAB_META_OFF + 16
+(REC_TE, REC_KPHI, REC_NTE_L2E, REC_SGN, REC_C_RE, REC_C_IM, REC_PW_RE, REC_PW_IM, REC_PF_RE, REC_PF_IM,
+ REC_TPW_RE, REC_TPW_IM, REC_TPF_RE, REC_TPF_IM) = range(14)
+
+
+def unpack_table(tab, ne):
+    """(nb, TAB_FLOATS) array/tensor -> dict of views: te, c, pw, pf (complex parts as (re, im) pairs), ap (nb,3,ne)."""
+    nb = tab.shape[0]
+    rec = tab[:, :TAB_AP_OFF].reshape(nb, MAX_NE, REC_FLOATS)[:, :ne]
+    ap = tab[:, TAB_AP_OFF:TAB_META_OFF].reshape(nb, 3, MAX_NE)[:, :, :ne]
+    return {"te": rec[:, :, REC_TE], "c": (rec[:, :, REC_C_RE], rec[:, :, REC_C_IM]),
+            "pw": (rec[:, :, REC_PW_RE], rec[:, :, REC_PW_IM]), "pf": (rec[:, :, REC_PF_RE], rec[:, :, REC_PF_IM]),
+            "ap": ap, "rec": rec}
 MODEL_WFPM, MODEL_FFPD, MODEL_MAGPHA = 0, 1, 2
 F_PHASE_CONSTRAINT, F_FLAT, F_ONLY_MAG, F_NO_RELU = 1, 2, 4, 8
 

@@ -18,7 +18,7 @@
  *    (NULL = legacy default stream).  Calls are asynchronous on that stream, allocate nothing and keep
  *    no global mutable state; the only host-side state is a thread-local error string.
  *  - Per-sample constants (echo times, fat phasor c_e = M[e,1], pseudo-inverse rows) live in a table
- *    of IG_TAB_FLOATS floats per sample built by ig_gen_tables from the (nb, ne) echo times.
+ *    of IG_TAB_FLOATS floats per sample (16-byte aligned) built by ig_gen_tables from the (nb, ne) echo times.
  *  - Return value: 0 ok; <0 invalid argument (IG_E_*); >0 a cudaError_t.  Never throws.
  *  - `ne` <= IG_MAX_NE.  Optional outputs may be NULL.
  */
@@ -33,23 +33,27 @@ extern "C" {
 
 #define IG_VERSION 100          /* 0.1.0 */
 #define IG_MAX_NE 16
-#define IG_TAB_ROWS 12
-#define IG_TAB_FLOATS (IG_TAB_ROWS * IG_MAX_NE)
+#define IG_REC_FLOATS 16                                   /* one record per echo                     */
+#define IG_TAB_AP_OFF (IG_MAX_NE * IG_REC_FLOATS)          /* A^+ rows: 3 x IG_MAX_NE                 */
+#define IG_TAB_META_OFF (IG_TAB_AP_OFF + 3 * IG_MAX_NE)    /* [0] = ne, [1] = field                   */
+#define IG_TAB_FLOATS (IG_TAB_META_OFF + 16)               /* 320 floats = 1280 B per sample          */
 
-/* table rows (each IG_MAX_NE floats, zero padded beyond ne) */
+/* Per-sample table = IG_MAX_NE echo records (zero beyond ne) + A^+ + meta.  Fields of an echo record: */
 enum {
-    IG_ROW_TE = 0,      /* echo time [s]                                                        */
-    IG_ROW_C_RE = 1,    /* fat phasor c_e = sum_p alpha_p exp(2 pi i te field f_p)  (M[e,1])     */
-    IG_ROW_C_IM = 2,
-    IG_ROW_PW_RE = 3,   /* pseudo-inverse row for water  M^+[0,e]                                */
-    IG_ROW_PW_IM = 4,
-    IG_ROW_PF_RE = 5,   /* pseudo-inverse row for fat    M^+[1,e]                                */
-    IG_ROW_PF_IM = 6,
-    IG_ROW_AP0 = 7,     /* A^+[0..2, e]: pseudo-inverse of the magnitude design matrix (gen_A)   */
-    IG_ROW_AP1 = 8,
-    IG_ROW_AP2 = 9,
-    IG_ROW_META = 10,   /* [0] = ne, [1] = field                                                 */
-    IG_ROW_RESERVED = 11
+    IG_REC_TE = 0,       /* echo time [s]                                                            */
+    IG_REC_KPHI = 1,     /* te * fm_sc: phase in TURNS per unit of the phi/300 map                    */
+    IG_REC_NTE_L2E = 2,  /* -te * log2(e): log2 of the decay per unit of R2* [1/s]                    */
+    IG_REC_SGN = 3,      /* (-1)^e, e = 1..ne: bipolar odd/even sign                                  */
+    IG_REC_C_RE = 4,     /* fat phasor c_e = sum_p alpha_p exp(2 pi i te field f_p)      (M[e,1])     */
+    IG_REC_C_IM = 5,
+    IG_REC_PW_RE = 6,    /* pseudo-inverse row for water  M^+[0,e]                                    */
+    IG_REC_PW_IM = 7,
+    IG_REC_PF_RE = 8,    /* pseudo-inverse row for fat    M^+[1,e]                                    */
+    IG_REC_PF_IM = 9,
+    IG_REC_TPW_RE = 10,  /* te * M^+[0,e]                                                             */
+    IG_REC_TPW_IM = 11,
+    IG_REC_TPF_RE = 12,  /* te * M^+[1,e]                                                             */
+    IG_REC_TPF_IM = 13
 };
 
 enum { IG_MODEL_WFPM = 0, IG_MODEL_FFPD = 1, IG_MODEL_MAGPHA = 2 };

@@ -49,15 +49,20 @@ def test_host_tables_match_reference(golden, case):
     nb, ne = te.shape
     tab = np.zeros((nb, L.TAB_FLOATS), np.float32)
     L.check(L.load().ig_gen_tables_host(te.ctypes.data, nb, ne, float(g[case + "_field"]), tab.ctypes.data), "tables")
-    t = tab.reshape(nb, L.TAB_ROWS, L.MAX_NE)
-    assert_close(t[:, L.ROW_TE, :ne], te, 0)
-    c = t[:, L.ROW_C_RE, :ne] + 1j * t[:, L.ROW_C_IM, :ne]
+    u = L.unpack_table(tab, ne)
+    assert_close(u["te"], te, 0)
+    c = u["c"][0] + 1j * u["c"][1]
     assert_close(c, g[case + "_M"][:, :, 1], 2e-6, "fat phasor")
     assert np.all(g[case + "_M"][:, :, 0] == 1)
-    pw = t[:, L.ROW_PW_RE, :ne] + 1j * t[:, L.ROW_PW_IM, :ne]
-    pf = t[:, L.ROW_PF_RE, :ne] + 1j * t[:, L.ROW_PF_IM, :ne]
+    pw = u["pw"][0] + 1j * u["pw"][1]
+    pf = u["pf"][0] + 1j * u["pf"][1]
     assert_close(np.stack([pw, pf], 1), g[case + "_Mpinv"], 3e-6, "M pinv")
-    ap = t[:, L.ROW_AP0:L.ROW_AP2 + 1, :ne]
-    assert_close(ap, g[case + "_Apinv"], 2e-5 if ne > 3 else 5e-3, "A pinv")     # ne == 3: square, ill-conditioned
-    assert not t[:, :L.ROW_META, ne:].any()                                      # zero padding beyond ne
-    assert np.all(t[:, L.ROW_META, 0] == ne)
+    assert_close(u["ap"], g[case + "_Apinv"], 2e-5 if ne > 3 else 5e-3, "A pinv")     # ne == 3: square, ill-conditioned
+    rec = u["rec"]
+    assert_close(rec[:, :, L.REC_TPW_RE] + 1j * rec[:, :, L.REC_TPW_IM], te * pw, 2e-7)
+    assert_close(rec[:, :, L.REC_KPHI], te * 300.0, 2e-7)
+    assert_close(rec[:, :, L.REC_NTE_L2E], -te * np.log2(np.e), 2e-7)
+    assert np.all(rec[:, :, L.REC_SGN] == np.where(np.arange(ne) % 2 == 0, -1.0, 1.0))
+    full = tab[:, :L.TAB_AP_OFF].reshape(nb, L.MAX_NE, L.REC_FLOATS)
+    assert not full[:, ne:].any()                                                # zero padding beyond ne
+    assert np.all(tab[:, L.TAB_META_OFF] == ne)
