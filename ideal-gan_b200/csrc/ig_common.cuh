@@ -212,12 +212,15 @@ template <int NE> struct SampleTab {
 
 // Straight 16-byte copy of the sample's first NE echo records (records beyond `ne` are zero in the global
 // table); the one r2_sc-dependent field is scaled on the way.  Only NE*4 threads take part.
-template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, const float *__restrict__ tab_b, int ne, float r2_sc) {
+template <int NE> __device__ __forceinline__ void stage_table_nosync(SampleTab<NE> &t, const float *__restrict__ tab_b, float r2_sc) {
     if (threadIdx.x < NE * 4) {
         float4 v = __ldg(reinterpret_cast<const float4 *>(tab_b) + threadIdx.x);
         if ((threadIdx.x & 3) == 0) v.z *= r2_sc;
         reinterpret_cast<float4 *>(t.r)[threadIdx.x] = v;
     }
+}
+template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, const float *__restrict__ tab_b, int ne, float r2_sc) {
+    stage_table_nosync(t, tab_b, r2_sc);
     __syncthreads();
 }
 
@@ -225,7 +228,7 @@ template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, 
 // loss reduction: per-thread partial -> warp shuffle -> block -> one float per block in scratch; the
 // last block to finish (ticket counter) adds the per-block partials in a fixed order in fp64 and
 // writes the scalar, then re-zeroes the ticket so the scratch can be reused by the next launch.
-// scratch layout: [0] unsigned ticket, [16..] float partials[gridDim.x * gridDim.y]
+// scratch layout: [0] unsigned ticket, [4] unsigned dynamic tile counter, [16..] float partials[gridDim.x * gridDim.y]
 // ------------------------------------------------------------------------------------------------
 constexpr size_t kScratchHeader = 16;
 
@@ -262,9 +265,47 @@ __device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float 
         double s = 0.0;
         for (int w = 0; w < nwarp; ++w) s += dpart[w];
         loss_out[0] = static_cast<float>(s * static_cast<double>(scale));
-        *ticket = 0u;
+        ticket[0] = 0u;
+        ticket[1] = 0u;      // dynamic tile counter of the persistent kernels
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copies + mbarrier pipeline (sm_90+/sm_100a PTX; shows up as UBLKCP / SYNCS in SASS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "IG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra IG_DONE_%=;\n"
+        "bra IG_WAIT_%=;\n"
+        "IG_DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// barrier among the first `count` threads of the block (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void named_barrier(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
 // NE buckets: kernels are instantiated for these echo counts; a call with `ne` echoes runs in the
 // smallest bucket >= ne with the unused echoes predicated off (their table entries are zero).

@@ -570,6 +570,170 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
 }
 
+// =================================================================================================
+// TMA-pipelined variant of the fused objective (packed path, no materialised outputs): the headline kernel.
+//
+// Warp-specialised persistent blocks: 8 consumer warps + 1 producer warp.  The producer's lane 0 streams
+// each tile (ne echo planes + the PM row, 512 voxels = 4 KB per plane) into a ring of shared-memory
+// stages with cp.async.bulk (TMA) completing on a "full" mbarrier; consumers read their 16 bytes per
+// plane with conflict-free LDS.128, and release the stage through an "empty" mbarrier as soon as pass 1
+// has turned the raw echoes into registers.  Loads therefore cost the consumers no registers, no address
+// arithmetic and no long-scoreboard stalls, and up to STAGES tiles per block are in flight to HBM.
+// =================================================================================================
+constexpr int kTileVox = kThreads * 2;                 // voxels per tile (two per consumer thread)
+constexpr int kPlaneBytes = kTileVox * 8;              // one complex plane of a tile
+template <int NE, int STAGES> struct TmaCfg {
+    static constexpr int tab_bytes = NE * IG_REC_FLOATS * 4;                      // the sample's echo records ride along with the tile
+    static constexpr int stage_bytes = (NE + 1) * kPlaneBytes + ((tab_bytes + 127) / 128) * 128;
+    static constexpr int smem_bytes = STAGES * stage_bytes;
+};
+
+// Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
+// cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
+template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
+    extern __shared__ __align__(128) unsigned char stage_mem[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+    __shared__ int stage_tile[STAGES];
+    const int nv = p.nv, ne = p.ne;
+    const int tiles_ps = (nv + kTileVox - 1) / kTileVox;
+    const int total = p.nb * tiles_ps;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    float loss_part = 0.f;
+    if (threadIdx.x >= kThreads) {
+        // ---------------- producer warp ----------------
+        if (threadIdx.x == kThreads) {
+            unsigned *next_tile = reinterpret_cast<unsigned *>(p.scratch) + 1;
+            for (int it = 0;; ++it) {
+                const int s = it % STAGES;
+                const int tile = static_cast<int>(atomicAdd(next_tile, 1u));
+                if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+                stage_tile[s] = tile;
+                if (tile >= total) {
+                    mbar_arrive(&full_bar[s]);                 // end marker: completes the phase without data
+                    break;
+                }
+                const int b = tile / tiles_ps;
+                const int vs = (tile - b * tiles_ps) * kTileVox;
+                const int nvox = (nv - vs < kTileVox) ? nv - vs : kTileVox;
+                const uint32_t bytes = static_cast<uint32_t>(nvox) * 8u;
+                unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
+                mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + TmaCfg<NE, STAGES>::tab_bytes);
+                const float *src = p.acqs + (static_cast<size_t>(b) * ne * nv + vs) * 2;
+                for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + static_cast<size_t>(e) * nv * 2, bytes, &full_bar[s]);
+                bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
+                bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, TmaCfg<NE, STAGES>::tab_bytes, &full_bar[s]);
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        const float r2_sc = p.r2_sc;
+        for (int it = 0;; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            const int tile = stage_tile[s];
+            if (tile >= total) break;
+            const int b = tile / tiles_ps;
+            const int vs = (tile - b * tiles_ps) * kTileVox;
+            const int v0 = vs + threadIdx.x * 2;
+            const bool active = v0 < nv;
+            unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
+            float4 *sraw = reinterpret_cast<float4 *>(stage) + threadIdx.x;
+            const SampleTab<NE> &T = *reinterpret_cast<const SampleTab<NE> *>(stage + (NE + 1) * kPlaneBytes);   // kdec = -te log2(e), unscaled
+            constexpr int kPlaneF4 = kPlaneBytes / 16;
+            const pk zero = splat<pk>(0.f);
+            AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (e < ne) {
+                        RawEcho<pk> raw;
+                        raw.v = sraw[e * kPlaneF4];
+                        abs_range(ar, raw);
+                    }
+                }
+            }
+            // background: every component of every voxel of the warp is exactly zero -> loss 0, gradient 0
+            if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
+                if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
+                continue;
+            }
+            const bool warp_ragged = __any_sync(0xffffffffu, active && is_ragged(ar));
+            pk phi_t = zero, r2s = zero;                       // r2s = R2* in 1/s
+            if (active) {
+                const float4 m4 = sraw[ne * kPlaneF4];
+                phi_t = mk(m4.x, m4.z);
+                r2s = vmul(r2_sc, mk(m4.y, m4.w));
+            }
+            if (active && !warp_ragged) {
+                pk d2[NE];
+                cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (e < ne) {
+                        const EchoRec R = T.r[e];
+                        const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
+                        d2[e] = vmul(m.d, m.d);
+                        RawEcho<pk> raw;
+                        raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
+                        const cx<pk> y = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
+                        // park y in this thread's own 16 bytes of the stage (the raw echo is no longer needed)
+                        sraw[e * kPlaneF4] = make_float4(y.re.d.x, y.re.d.y, y.im.d.x, y.im.d.y);
+                        cmac(rw, R.pw_re, R.pw_im, y);
+                        cmac(rf, R.pf_re, R.pf_im, y);
+                        cmac(tw, R.tpw_re, R.tpw_im, y);
+                        cmac(tf, R.tpf_re, R.tpf_im, y);
+                    }
+                }
+                pk lsum = zero;
+                cx<pk> K = czero<pk>();
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    if (e < ne) {
+                        const EchoRec R = T.r[e];
+                        const float4 yv = sraw[e * kPlaneF4];
+                        const cx<pk> y{mk(yv.x, yv.y), mk(yv.z, yv.w)};
+                        const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                        const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
+                        const cx<pk> r{vsub(yhat.re, y.re), vsub(yhat.im, y.im)};
+                        const cx<pk> w{vmul(d2[e], r.re), vmul(d2[e], r.im)};
+                        lsum = vfma(w.re, r.re, lsum);
+                        lsum = vfma(w.im, r.im, lsum);
+                        const cx<pk> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
+                        K.re = vfma(w.re, g.re, K.re);
+                        K.re = vfma(w.im, g.im, K.re);
+                        K.im = vfma(w.re, g.im, K.im);
+                        K.im = vfma(vneg(w.im), g.re, K.im);
+                    }
+                }
+                loss_part += hsum(lsum);
+                st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<pk>{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * r2_sc * p.inv_n, K.re)});
+            } else if (active) {
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    float ls, gphi, gr2;
+                    // the table in the stage carries the unscaled decay constant: hand the slow path R2* in 1/s
+                    a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
+                                            r2_sc, ls, gphi, gr2);
+                    loss_part += ls;
+                    reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+                }
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);          // this warp no longer touches the stage
+        }
+    }
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+}
+
 // -------------------------------------------------------------------------------------------------
 // launch helpers
 // -------------------------------------------------------------------------------------------------
@@ -609,6 +773,20 @@ template <typename K1, typename K2> static int launch_persistent(bool packed, co
         if (int rc = persistent_grid(ks, p.nb, p.nv, 1, &grid)) return rc;
         ks<<<grid, kThreads, 0, st>>>(p);
     }
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename K> static int launch_tma(const SolveParams &p, cudaStream_t st, K kernel, int smem) {
+    int dev = 0, sms = 0, occ = 0;
+    IG_CUDA(cudaGetDevice(&dev));
+    IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads + 32, smem));
+    const long tiles = static_cast<long>(p.nb) * ((p.nv + kTileVox - 1) / kTileVox);
+    long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
+    if (g > tiles) g = tiles;
+    kernel<<<static_cast<int>(g), kThreads + 32, smem, st>>>(p);
     IG_CUDA(cudaGetLastError());
     return 0;
 }
@@ -712,6 +890,17 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
+        static const int no_tma = [] { const char *e = getenv("IG_A2A_NO_TMA"); return e ? atoi(e) : 0; }();         // tuning knobs
+        static const int tma_occ = [] { const char *e = getenv("IG_A2A_TMA_OCC"); return e ? atoi(e) : 3; }();
+        if (packed && !no_tma) {
+            // (blocks per SM, stages) chosen so that blocks * stages * stage_bytes fits the 227 KB of shared memory
+            constexpr int kBudget = 216 * 1024;
+            if (tma_occ >= 3 && 3 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 3, 2>, TmaCfg<NE, 2>::smem_bytes);
+            if (tma_occ == 1 && TmaCfg<NE, 4>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 4>, TmaCfg<NE, 4>::smem_bytes);
+            if (2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3>, TmaCfg<NE, 3>::smem_bytes);
+            if (2 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 2>, TmaCfg<NE, 2>::smem_bytes);
+            return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 3>, TmaCfg<NE, 3>::smem_bytes);
+        }
         static const int occ3 = [] { const char *e = getenv("IG_A2A_OCC3"); return e ? atoi(e) : 0; }();     // tuning knob
         if (occ3) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 3>, a2a_loss_kernel<NE, float, false, 3>);
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);

@@ -195,8 +195,9 @@ def test_acq_to_acq_and_config2_loss_vs_reference_vectors(golden, name):
     assert_close(host(gl), g[name + "_loss_gpm"], TOL, "loss grad pm")
     assert_close(host(shat2), g[name + "_out"], TOL)
     assert_close(host(rho2), host(rho), 1e-6)
-    loss_b, gl_b, _, _ = ops.a2a_loss(a, p, tab)
-    assert loss_b.item() == loss.item() and torch.equal(gl_b, gl)
+    loss_b, gl_b, _, _ = ops.a2a_loss(a, p, tab)       # no materialised outputs -> the TMA-pipelined kernel
+    assert abs(loss_b.item() - loss.item()) <= 1e-6 * loss.item()
+    assert_close(host(gl_b), host(gl), 1e-6)
 
 
 @pytest.mark.parametrize("hw", [(9, 7), (48, 64)])
@@ -214,7 +215,10 @@ def test_acq_to_acq_family_vs_oracle(hw, ne):
         rho_r, s_r = orc.acq_to_acq(a, p, te=cpu(te), only_mag=only_mag)
         up_r, up_s = rng.standard_normal(rho_r.shape).astype(np.float32), rng.standard_normal(s_r.shape).astype(np.float32)
         ga_r, gp_r = torch.autograd.grad((rho_r * cpu(up_r)).sum() + (s_r * cpu(up_s)).sum(), [a, p])
-        # d|S_hat| at S_hat = 0 (background) is NaN in autodiff (0 * inf); the kernel defines it as 0
+        # d|S_hat| at S_hat = 0 (background) is NaN in autodiff (0 * inf) and poisons that voxel's gradients; the
+        # kernel defines the derivative as 0 there, so background voxels are compared for finiteness only
+        fin_a, fin_p = host(torch.isfinite(ga_r)), host(torch.isfinite(gp_r))
+        assert only_mag or (fin_a.all() and fin_p.all())
         ga_r, gp_r = torch.nan_to_num(ga_r, nan=0.0), torch.nan_to_num(gp_r, nan=0.0)
         tab = ops.gen_tables(dev(te), 1.5)
         flags = L.F_ONLY_MAG if only_mag else 0
@@ -222,8 +226,9 @@ def test_acq_to_acq_family_vs_oracle(hw, ne):
         assert_close(host(rho), host(rho_r), TOL, "rho")
         assert_close(host(shat), host(s_r), TOL, "S_hat")
         ga, gp = ops.a2a_bwd(dev(acqs), dev(pm), tab, dev(up_r), dev(up_s), flags=flags)
-        assert_close(host(ga), host(ga_r), TOL, "grad acqs")
-        assert_close(host(gp), host(gp_r), TOL, "grad pm")
+        assert np.isfinite(host(ga)).all() and np.isfinite(host(gp)).all()
+        assert_close(host(ga) * fin_a, host(ga_r), TOL, "grad acqs")
+        assert_close(host(gp) * fin_p, host(gp_r), TOL, "grad pm")
     # fused objective, including the per-component mask (ragged voxels -> slow path)
     acqs2 = acqs.copy()
     acqs2[0, 0, H // 2, W // 2, 1] = 0.0
@@ -232,8 +237,15 @@ def test_acq_to_acq_family_vs_oracle(hw, ne):
     lref, _, _ = orc.physics_loss_a2a(cpu(acqs2), p2, te=cpu(te))
     (gref,) = torch.autograd.grad(lref, [p2])
     loss, gl, _, _ = ops.a2a_loss(dev(acqs2), dev(pm), tab)
-    assert abs(loss.item() - lref.item()) <= TOL * lref.item()
-    assert_close(host(gl), host(gref), TOL, "loss grad pm")
+    if ne == 2:
+        # two echoes, two unknowns: the fit is exact wherever nothing is masked, so the objective is rounding noise
+        # except at the voxels whose components were zeroed above; compare on the absolute scale of the data
+        scale = float((acqs2 ** 2).mean())
+        assert abs(loss.item() - lref.item()) <= TOL * scale
+        assert np.abs(host(gl) - host(gref)).max() <= TOL * max(np.abs(host(gref)).max(), scale)
+    else:
+        assert abs(loss.item() - lref.item()) <= TOL * lref.item()
+        assert_close(host(gl), host(gref), TOL, "loss grad pm")
 
 
 def test_full_size_properties():
