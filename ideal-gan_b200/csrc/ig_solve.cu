@@ -22,6 +22,7 @@ struct SolveParams {
     void *scratch;
     long pm_bstride, bip_bstride;
     int nb, ne, nv, flags;
+    int tile_stride;      // persistent kernels: visit a sample's tiles in the order (j * tile_stride) % tiles_per_sample
     float r2_sc, inv_n;
 };
 
@@ -590,11 +591,12 @@ template <int NE, int STAGES> struct TmaCfg {
 
 // Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
 // cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
-template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
+template <int NE, int MINB, int STAGES, bool EXACT> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
-    __shared__ int stage_tile[STAGES];
-    const int nv = p.nv, ne = p.ne;
+    __shared__ int2 stage_tile[STAGES];             // (sample, first voxel) of the tile in each stage; sample < 0 = end
+    __shared__ int chunk_ctr;                       // consumer warps draw 64-voxel chunks of the ring from here
+    const int nv = p.nv, ne = EXACT ? NE : p.ne;
     const int tiles_ps = (nv + kTileVox - 1) / kTileVox;
     const int total = p.nb * tiles_ps;
     if (threadIdx.x == 0) {
@@ -602,6 +604,7 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kThreads / 32);
         }
+        chunk_ctr = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -610,41 +613,59 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
         // ---------------- producer warp ----------------
         if (threadIdx.x == kThreads) {
             unsigned *next_tile = reinterpret_cast<unsigned *>(p.scratch) + 1;
+            const size_t plane_stride = static_cast<size_t>(nv) * 2;
+            // Tiles of a sample are visited in a strided order so that cheap background tiles (load-bound) and tissue
+            // tiles (math-bound) are in flight together chip-wide instead of in alternating phases.
+            auto claim = [&]() -> int2 {
+                const int k = static_cast<int>(atomicAdd(next_tile, 1u));
+                if (k >= total) return make_int2(-1, 0);
+                const int b = k / tiles_ps;
+                const int j = k - b * tiles_ps;
+                const int vs = static_cast<int>((static_cast<unsigned long long>(j) * static_cast<unsigned>(p.tile_stride)) % static_cast<unsigned>(tiles_ps)) * kTileVox;
+                return make_int2(b, vs);
+            };
             for (int it = 0;; ++it) {
                 const int s = it % STAGES;
-                const int tile = static_cast<int>(atomicAdd(next_tile, 1u));
+                const int2 cur = claim();
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-                stage_tile[s] = tile;
-                if (tile >= total) {
+                stage_tile[s] = cur;
+                if (cur.x < 0) {
                     mbar_arrive(&full_bar[s]);                 // end marker: completes the phase without data
                     break;
                 }
-                const int b = tile / tiles_ps;
-                const int vs = (tile - b * tiles_ps) * kTileVox;
+                const int b = cur.x, vs = cur.y;
                 const int nvox = (nv - vs < kTileVox) ? nv - vs : kTileVox;
                 const uint32_t bytes = static_cast<uint32_t>(nvox) * 8u;
                 unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
                 mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + TmaCfg<NE, STAGES>::tab_bytes);
                 const float *src = p.acqs + (static_cast<size_t>(b) * ne * nv + vs) * 2;
-                for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + static_cast<size_t>(e) * nv * 2, bytes, &full_bar[s]);
+                for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + e * plane_stride, bytes, &full_bar[s]);
                 bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
                 bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, TmaCfg<NE, STAGES>::tab_bytes, &full_bar[s]);
             }
         }
     } else {
         // ---------------- consumer warps ----------------
+        // Warps are decoupled: each draws the next 64-voxel chunk (1/8 of a tile) from a shared counter, so a warp
+        // that lands on background (skipped in ~40 instructions) immediately moves on instead of idling until the
+        // tissue warps of its tile finish.  A stage returns to the producer when its 8 chunks have been released.
+        constexpr int kChunks = kThreads / 32;
         const float r2_sc = p.r2_sc;
-        for (int it = 0;; ++it) {
+        const int lane = threadIdx.x & 31;
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&chunk_ctr, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            const int it = g / kChunks, slot = (g % kChunks) * 32 + lane;
             const int s = it % STAGES;
             mbar_wait(&full_bar[s], (it / STAGES) & 1);
-            const int tile = stage_tile[s];
-            if (tile >= total) break;
-            const int b = tile / tiles_ps;
-            const int vs = (tile - b * tiles_ps) * kTileVox;
-            const int v0 = vs + threadIdx.x * 2;
+            const int2 where = stage_tile[s];
+            if (where.x < 0) break;
+            const int b = where.x, vs = where.y;
+            const int v0 = vs + slot * 2;
             const bool active = v0 < nv;
             unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
-            float4 *sraw = reinterpret_cast<float4 *>(stage) + threadIdx.x;
+            float4 *sraw = reinterpret_cast<float4 *>(stage) + slot;
             const SampleTab<NE> &T = *reinterpret_cast<const SampleTab<NE> *>(stage + (NE + 1) * kPlaneBytes);   // kdec = -te log2(e), unscaled
             constexpr int kPlaneF4 = kPlaneBytes / 16;
             const pk zero = splat<pk>(0.f);
@@ -652,7 +673,7 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
             if (active) {
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
-                    if (e < ne) {
+                    if (EXACT || e < ne) {
                         RawEcho<pk> raw;
                         raw.v = sraw[e * kPlaneF4];
                         abs_range(ar, raw);
@@ -663,7 +684,7 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
             if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
                 if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
                 __syncwarp();
-                if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
                 continue;
             }
             const bool warp_ragged = __any_sync(0xffffffffu, active && is_ragged(ar));
@@ -673,19 +694,21 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
                 phi_t = mk(m4.x, m4.z);
                 r2s = vmul(r2_sc, mk(m4.y, m4.w));
             }
-            if (active && !warp_ragged) {
-                pk d2[NE];
-                cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
+            pk d2[NE];
+            cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
+            const bool fast = active && !warp_ragged;
+            if (fast) {
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
-                    if (e < ne) {
+                    if (EXACT || e < ne) {
                         const EchoRec R = T.r[e];
                         const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
                         d2[e] = vmul(m.d, m.d);
                         RawEcho<pk> raw;
                         raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
                         const cx<pk> y = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
-                        // park y in this thread's own 16 bytes of the stage (the raw echo is no longer needed)
+                        // park y in this thread's own 16 bytes of the stage (the raw echo is no longer needed): 24 fewer
+                        // live registers across pass 2 than keeping it, for 6 STS + 6 LDS
                         sraw[e * kPlaneF4] = make_float4(y.re.d.x, y.re.d.y, y.im.d.x, y.im.d.y);
                         cmac(rw, R.pw_re, R.pw_im, y);
                         cmac(rf, R.pf_re, R.pf_im, y);
@@ -693,11 +716,13 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
                         cmac(tf, R.tpf_re, R.tpf_im, y);
                     }
                 }
+            }
+            if (fast) {
                 pk lsum = zero;
                 cx<pk> K = czero<pk>();
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
-                    if (e < ne) {
+                    if (EXACT || e < ne) {
                         const EchoRec R = T.r[e];
                         const float4 yv = sraw[e * kPlaneF4];
                         const cx<pk> y{mk(yv.x, yv.y), mk(yv.z, yv.w)};
@@ -728,7 +753,7 @@ template <int NE, int MINB, int STAGES> __global__ void __launch_bounds__(kThrea
                 }
             }
             __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[s]);          // this warp no longer touches the stage
+            if (lane == 0) mbar_arrive(&empty_bar[s]);                        // this warp no longer touches the stage
         }
     }
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
@@ -775,6 +800,15 @@ template <typename K1, typename K2> static int launch_persistent(bool packed, co
     }
     IG_CUDA(cudaGetLastError());
     return 0;
+}
+
+// a stride near 0.618 * n that is coprime with n: consecutive work items land on distant tiles of the slice
+static int coprime_stride(int n) {
+    if (n <= 2) return 1;
+    int s = static_cast<int>(n * 0.6180339887) | 1;
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    while (gcd(s, n) != 1) s += 2;
+    return s % n;
 }
 
 template <typename K> static int launch_tma(const SolveParams &p, cudaStream_t st, K kernel, int smem) {
@@ -890,19 +924,17 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
-        static const int no_tma = [] { const char *e = getenv("IG_A2A_NO_TMA"); return e ? atoi(e) : 0; }();         // tuning knobs
-        static const int tma_occ = [] { const char *e = getenv("IG_A2A_TMA_OCC"); return e ? atoi(e) : 3; }();
+        static const int no_tma = [] { const char *e = getenv("IG_A2A_NO_TMA"); return e ? atoi(e) : 0; }();         // A/B knob
         if (packed && !no_tma) {
-            // (blocks per SM, stages) chosen so that blocks * stages * stage_bytes fits the 227 KB of shared memory
+            // two blocks per SM with as many ring stages as fit the 227 KB of shared memory (measured: 2 x 3 stages at 96
+            // registers = 3 x 2 stages at 72 registers within noise for ne = 6; the former does not spill)
             constexpr int kBudget = 216 * 1024;
-            if (tma_occ >= 3 && 3 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 3, 2>, TmaCfg<NE, 2>::smem_bytes);
-            if (tma_occ == 1 && TmaCfg<NE, 4>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 4>, TmaCfg<NE, 4>::smem_bytes);
-            if (2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3>, TmaCfg<NE, 3>::smem_bytes);
-            if (2 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 2>, TmaCfg<NE, 2>::smem_bytes);
-            return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 3>, TmaCfg<NE, 3>::smem_bytes);
+            p.tile_stride = coprime_stride((nv + kTileVox - 1) / kTileVox);
+            if (ne == NE && NE <= 8 && 2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3, true>, TmaCfg<NE, 3>::smem_bytes);
+            if (2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3, false>, TmaCfg<NE, 3>::smem_bytes);
+            if (2 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 2, false>, TmaCfg<NE, 2>::smem_bytes);
+            return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 3, false>, TmaCfg<NE, 3>::smem_bytes);
         }
-        static const int occ3 = [] { const char *e = getenv("IG_A2A_OCC3"); return e ? atoi(e) : 0; }();     // tuning knob
-        if (occ3) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 3>, a2a_loss_kernel<NE, float, false, 3>);
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
 }
