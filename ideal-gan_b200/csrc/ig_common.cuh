@@ -225,6 +225,46 @@ template <int NE> __device__ __forceinline__ void stage_table(SampleTab<NE> &t, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-echo modulation shared by the solve-side kernels
+// ------------------------------------------------------------------------------------------------
+// demodulator for one echo: Wm = dinv * conj(u), Wp = d * u
+template <typename V> struct Mod {
+    V c, s, d, dinv;
+};
+template <int NE, typename V> __device__ __forceinline__ Mod<V> modulator(const SampleTab<NE> &T, int e, V phi_t, V r2, V bturn) {
+    Mod<V> m;
+    unit_phasor(vfma(T.r[e].sgn, bturn, vmul(T.r[e].kphi, phi_t)), m.c, m.s);
+    const V lg = vmul(T.r[e].kdec, r2);
+    m.d = fast_ex2(lg);
+    m.dinv = fast_ex2(vneg(lg));
+    return m;
+}
+template <typename V> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
+    Mod<V> m;
+    unit_phasor(vfma(R.sgn, bturn, vmul(R.kphi, phi_t)), m.c, m.s);
+    const V lg = vmul(R.kdec, r2);
+    m.d = fast_ex2(lg);
+    m.dinv = fast_ex2(vneg(lg));
+    return m;
+}
+template <typename V> __device__ __forceinline__ cx<V> demod(const Mod<V> &m, const cx<V> &S) {       // Wm S
+    const cx<V> t{vfma(m.s, S.im, vmul(m.c, S.re)), vfma(vneg(m.s), S.re, vmul(m.c, S.im))};
+    return cscale(m.dinv, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> remod(const Mod<V> &m, const cx<V> &y) {       // Wp y
+    const cx<V> t{vfma(vneg(m.s), y.im, vmul(m.c, y.re)), vfma(m.s, y.re, vmul(m.c, y.im))};
+    return cscale(m.d, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> remod_inv(const Mod<V> &m, const cx<V> &g) {   // conj(Wm) g = dinv u g
+    const cx<V> t{vfma(vneg(m.s), g.im, vmul(m.c, g.re)), vfma(m.s, g.re, vmul(m.c, g.im))};
+    return cscale(m.dinv, t);
+}
+template <typename V> __device__ __forceinline__ cx<V> demod_fwd(const Mod<V> &m, const cx<V> &G) {   // conj(Wp) G = d conj(u) G
+    const cx<V> t{vfma(m.s, G.im, vmul(m.c, G.re)), vfma(vneg(m.s), G.re, vmul(m.c, G.im))};
+    return cscale(m.d, t);
+}
+
+// ------------------------------------------------------------------------------------------------
 // loss reduction: per-thread partial -> warp shuffle -> block -> one float per block in scratch; the
 // last block to finish (ticket counter) adds the per-block partials in a fixed order in fp64 and
 // writes the scalar, then re-zeroes the ticket so the scratch can be reused by the next launch.

@@ -1,0 +1,486 @@
+// Second-tier operators of the reference's physics library: the magnitude-only fit with its
+// closed-form 2x2 eigen-decomposition, the signal-domain and parameter-domain uncertainty propagation, and PDFF
+// extraction.  All are one thread per voxel, every echo in registers, per-sample tables in shared memory; none of
+// them materialises the (nb, ne, nv) intermediates -- or, for PDFF_uncertainty, the (nv, nb, ne, ne) diagonal
+// matrices -- that the TensorFlow op chains of /root/reference/wflib/IDEAL_model.py:100-138, 314-401, 628-767 do.
+#include "ig_common.cuh"
+
+namespace ig {
+
+constexpr float kEigEps = 1e-12f;        // IDEAL_model.py:107
+
+struct Eig {
+    float x, y, ratio;
+};
+
+// principal eigenpair of [[a, b/2], [b/2, c]]  (IDEAL_model.py:100-138)
+__device__ __forceinline__ Eig eig_fwd(float a, float b, float c) {
+    const float hd = (a - c) * 0.5f, hb = b * 0.5f;
+    const float delta = sqrtf(hd * hd + hb * hb + kEigEps);
+    const float mean = (a + c) * 0.5f;
+    const float lmax = mean + delta, lmin = mean - delta;
+    const float lmax_p = fmaxf(lmax, 0.f), lmin_p = fmaxf(lmin, 0.f);
+    const float vx = hb, vy = lmax - a;
+    const float norm = sqrtf(vx * vx + vy * vy + kEigEps);
+    const float scale = sqrtf(lmax_p);
+    Eig r;
+    r.x = scale * (vx / norm);
+    r.y = scale * (vy / norm);
+    r.ratio = lmax_p > 0.f ? lmin_p / lmax_p : 0.f;
+    return r;
+}
+
+// adjoint of eig_fwd: upstream (gx, gy, gr) -> (ga, gb, gc)
+__device__ __forceinline__ void eig_bwd(float a, float b, float c, float gx, float gy, float gr, float &ga, float &gb, float &gc) {
+    const float hd = (a - c) * 0.5f, hb = b * 0.5f;
+    const float delta = sqrtf(hd * hd + hb * hb + kEigEps);
+    const float mean = (a + c) * 0.5f;
+    const float lmax = mean + delta, lmin = mean - delta;
+    const float lmax_p = fmaxf(lmax, 0.f), lmin_p = fmaxf(lmin, 0.f);
+    const float vx = hb, vy = lmax - a;
+    const float norm = sqrtf(vx * vx + vy * vy + kEigEps);
+    const float inv_norm = 1.0f / norm;
+    const float scale = sqrtf(lmax_p);
+    const float vxn = vx * inv_norm, vyn = vy * inv_norm;
+    const float g_scale = gx * vxn + gy * vyn;
+    const float g_vxn = gx * scale, g_vyn = gy * scale;
+    const float dot = (g_vxn * vx + g_vyn * vy) * inv_norm * inv_norm * inv_norm;
+    float g_vx = g_vxn * inv_norm - dot * vx;
+    const float g_vy = g_vyn * inv_norm - dot * vy;
+    float g_lmax = g_vy, g_lmin = 0.f;
+    if (lmax > 0.f) {
+        g_lmax += g_scale * 0.5f / scale;
+        g_lmax += -gr * lmin_p / (lmax_p * lmax_p);
+        if (lmin > 0.f) g_lmin = gr / lmax_p;
+    }
+    const float g_mean = g_lmax + g_lmin, g_delta = g_lmax - g_lmin;
+    const float g_hd = g_delta * hd / delta;
+    g_vx += g_delta * hb / delta;
+    ga = 0.5f * g_mean + 0.5f * g_hd - g_vy;
+    gc = 0.5f * g_mean - 0.5f * g_hd;
+    gb = 0.5f * g_vx;
+}
+
+__global__ void eigenvals_kernel(const float *__restrict__ X, long n, float *__restrict__ xy, float *__restrict__ ratio) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Eig e = eig_fwd(X[3 * i], X[3 * i + 1], X[3 * i + 2]);
+    xy[2 * i] = e.x;
+    xy[2 * i + 1] = e.y;
+    ratio[i] = e.ratio;
+}
+
+__global__ void eigenvals_bwd_kernel(const float *__restrict__ X, long n, const float *__restrict__ g_xy, const float *__restrict__ g_ratio,
+                                     float *__restrict__ gX) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ga, gb, gc;
+    eig_bwd(X[3 * i], X[3 * i + 1], X[3 * i + 2], g_xy ? g_xy[2 * i] : 0.f, g_xy ? g_xy[2 * i + 1] : 0.f, g_ratio ? g_ratio[i] : 0.f, ga, gb, gc);
+    gX[3 * i] = ga;
+    gX[3 * i + 1] = gb;
+    gX[3 * i + 2] = gc;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// CSE_mag: y_e = (e^{te R} |S_e|)^2 ; abc = A^+ y ; fit = A abc ; S_hat_e = e^{-te R} sqrt(fit_e) [fit > 1e-6]
+// -------------------------------------------------------------------------------------------------------------
+struct CseParams {
+    const float *mag, *r2, *r2nu, *tab;                 // (nb, ne, nv), (nb, nv), optional (nb, nv)
+    float *rho, *fit, *demod, *ls, *unc;                // forward outputs (all optional)
+    const float *g_rho, *g_fit, *g_demod, *g_ls, *g_unc;   // backward upstreams (all optional)
+    float *g_mag, *g_r2, *g_r2nu;
+    int nb, ne, nv;
+    float r2_sc;
+};
+
+template <int NE> struct MagTab {
+    float te[NE], a1[NE], a2[NE], p0[NE], p1[NE], p2[NE];      // A_e = (1, a1, a2) ; A^+[:, e] = (p0, p1, p2)
+};
+template <int NE> __device__ __forceinline__ void stage_mag_table(MagTab<NE> &t, const float *tab_b, int ne) {
+    for (int e = threadIdx.x; e < NE; e += blockDim.x) {
+        const bool live = e < ne;
+        const float cr = live ? tab_b[e * IG_REC_FLOATS + IG_REC_C_RE] : 0.f, ci = live ? tab_b[e * IG_REC_FLOATS + IG_REC_C_IM] : 0.f;
+        t.te[e] = live ? tab_b[e * IG_REC_FLOATS + IG_REC_TE] : 0.f;
+        t.a1[e] = cr;
+        t.a2[e] = cr * cr + ci * ci;
+        t.p0[e] = live ? tab_b[IG_TAB_AP_OFF + 0 * IG_MAX_NE + e] : 0.f;
+        t.p1[e] = live ? tab_b[IG_TAB_AP_OFF + 1 * IG_MAX_NE + e] : 0.f;
+        t.p2[e] = live ? tab_b[IG_TAB_AP_OFF + 2 * IG_MAX_NE + e] : 0.f;
+    }
+    __syncthreads();
+}
+
+template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) cse_mag_kernel(const CseParams p) {
+    __shared__ MagTab<NE> T;
+    const int b = blockIdx.y;
+    stage_mag_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t eb = static_cast<size_t>(b) * ne * nv, vb = static_cast<size_t>(b) * nv;
+    const float R = p.r2[vb + v] * p.r2_sc;
+    float S[NE], y[NE], wm[NE];
+    float a = 0.f, bb = 0.f, c = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            S[e] = p.mag[eb + static_cast<size_t>(e) * nv + v];
+            wm[e] = __expf(T.te[e] * R);
+            const float t = wm[e] * S[e];
+            y[e] = t * t;
+            a = fmaf(T.p0[e], y[e], a);
+            bb = fmaf(T.p1[e], y[e], bb);
+            c = fmaf(T.p2[e], y[e], c);
+        }
+    }
+    const float inv_rho = 1.0f / kRhoSc, inv_rho2 = 1.0f / (kRhoSc * kRhoSc);
+    if constexpr (!BWD) {
+        const Eig eg = eig_fwd(a, bb, c);
+        if (p.rho) {
+            p.rho[(static_cast<size_t>(b) * 2 + 0) * nv + v] = eg.x * inv_rho;
+            p.rho[(static_cast<size_t>(b) * 2 + 1) * nv + v] = eg.y * inv_rho;
+        }
+        if (p.ls) {
+            p.ls[(static_cast<size_t>(b) * 3 + 0) * nv + v] = a * inv_rho2;
+            p.ls[(static_cast<size_t>(b) * 3 + 1) * nv + v] = bb * inv_rho2;
+            p.ls[(static_cast<size_t>(b) * 3 + 2) * nv + v] = c * inv_rho2;
+        }
+        if (p.unc) p.unc[vb + v] = eg.ratio;
+        const float Rnu = p.r2nu ? p.r2nu[vb + v] * p.r2_sc : 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const size_t o = eb + static_cast<size_t>(e) * nv + v;
+                if (p.fit) {
+                    const float f = fmaf(T.a2[e], c, fmaf(T.a1[e], bb, a));
+                    p.fit[o] = f > 1e-6f ? sqrtf(f) / wm[e] : 0.f;
+                }
+                if (p.demod) {
+                    if (p.r2nu) {
+                        const float t = __expf(T.te[e] * Rnu) * S[e];
+                        p.demod[o] = t * t;
+                    } else {
+                        p.demod[o] = y[e];
+                    }
+                }
+            }
+        }
+    } else {
+        float ga = 0.f, gb = 0.f, gc = 0.f;
+        {
+            const float gx = p.g_rho ? p.g_rho[(static_cast<size_t>(b) * 2 + 0) * nv + v] * inv_rho : 0.f;
+            const float gy = p.g_rho ? p.g_rho[(static_cast<size_t>(b) * 2 + 1) * nv + v] * inv_rho : 0.f;
+            const float gr = p.g_unc ? p.g_unc[vb + v] : 0.f;
+            if (p.g_rho || p.g_unc) eig_bwd(a, bb, c, gx, gy, gr, ga, gb, gc);
+        }
+        if (p.g_ls) {
+            ga += p.g_ls[(static_cast<size_t>(b) * 3 + 0) * nv + v] * inv_rho2;
+            gb += p.g_ls[(static_cast<size_t>(b) * 3 + 1) * nv + v] * inv_rho2;
+            gc += p.g_ls[(static_cast<size_t>(b) * 3 + 2) * nv + v] * inv_rho2;
+        }
+        float gR = 0.f, gRnu = 0.f;
+        if (p.g_fit) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (e < ne) {
+                    const float f = fmaf(T.a2[e], c, fmaf(T.a1[e], bb, a));
+                    if (f > 1e-6f) {                   // the reference's where(fit > 1e-6, sqrt(fit), 0): zero gradient elsewhere
+                        const float gf = p.g_fit[eb + static_cast<size_t>(e) * nv + v];
+                        const float sq = sqrtf(f), shat = sq / wm[e];
+                        const float gfit = gf * 0.5f / (sq * wm[e]);
+                        ga += gfit;
+                        gb = fmaf(gfit, T.a1[e], gb);
+                        gc = fmaf(gfit, T.a2[e], gc);
+                        gR = fmaf(-T.te[e] * gf, shat, gR);
+                    }
+                }
+            }
+        }
+        const float Rnu = p.r2nu ? p.r2nu[vb + v] * p.r2_sc : 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const size_t o = eb + static_cast<size_t>(e) * nv + v;
+                float gy = fmaf(T.p2[e], gc, fmaf(T.p1[e], gb, T.p0[e] * ga));
+                float gS = 0.f;
+                if (p.g_demod) {
+                    const float gd = p.g_demod[o];
+                    if (p.r2nu) {
+                        const float wn = __expf(T.te[e] * Rnu);
+                        gS = gd * 2.f * wn * wn * S[e];
+                        gRnu = fmaf(gd * 2.f * T.te[e], wn * wn * S[e] * S[e], gRnu);
+                    } else {
+                        gy += gd;
+                    }
+                }
+                gS = fmaf(gy * 2.f * wm[e], wm[e] * S[e], gS);
+                gR = fmaf(gy * 2.f * T.te[e], y[e], gR);
+                if (p.g_mag) p.g_mag[o] = gS;
+            }
+        }
+        if (p.g_r2) p.g_r2[vb + v] = gR * p.r2_sc;
+        if (p.g_r2nu) p.g_r2nu[vb + v] = gRnu * p.r2_sc;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// acq_uncertainty: Var_e = V_e |rho_W + c_e rho_F|^2,  V_e = 1 - e^{-(2 pi te)^2 s_phi} + e^{-te mu_R} te^2 s_R
+// -------------------------------------------------------------------------------------------------------------
+struct UncParams {
+    const float *rho, *phi_var, *r2_mean, *r2_var, *tab;   // (nb,2,nv,2), (nb,nv) x3 (r2_* NULL = rem_R2)
+    float *out;                                            // (nb, ne, nv, ch)
+    const float *g_out;
+    float *g_phi_var, *g_r2_mean, *g_r2_var;
+    int nb, ne, nv, ch;
+    float r2_sc;
+};
+
+template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) acq_unc_kernel(const UncParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, 1.0f);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.nv) return;
+    const int nv = p.nv, ne = p.ne, ch = p.ch;
+    const size_t vb = static_cast<size_t>(b) * nv + v;
+    const float2 w2 = reinterpret_cast<const float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 0) * nv + v];
+    const float2 f2 = reinterpret_cast<const float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 1) * nv + v];
+    const cx<float> rw{kRhoSc * w2.x, kRhoSc * w2.y}, rf{kRhoSc * f2.x, kRhoSc * f2.y};
+    const float s_phi = p.phi_var[vb] * (kFmSc * kFmSc);
+    const bool r2 = p.r2_mean != nullptr;
+    const float mu = r2 ? p.r2_mean[vb] * p.r2_sc : 0.f, s_r = r2 ? p.r2_var[vb] * (p.r2_sc * p.r2_sc) : 0.f;
+    float g_sphi = 0.f, g_mu = 0.f, g_sr = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const float te = T.r[e].te, k = kTwoPi * te, k2 = k * k;
+            const float ephi = __expf(-k2 * s_phi);
+            const float er = r2 ? __expf(-te * mu) * te * te : 0.f;
+            const cx<float> m = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
+            const float a2 = m.re * m.re + m.im * m.im;
+            const size_t o = ((static_cast<size_t>(b) * ne + e) * nv + v) * ch;
+            if constexpr (!BWD) {
+                const float var = (1.0f - ephi + er * s_r) * a2;
+                p.out[o] = var;
+                if (ch == 2) p.out[o + 1] = var;
+            } else {
+                const float g = (ch == 2 ? p.g_out[o] + p.g_out[o + 1] : p.g_out[o]) * a2;
+                g_sphi = fmaf(g * k2, ephi, g_sphi);
+                g_mu = fmaf(-g * te, er * s_r, g_mu);
+                g_sr = fmaf(g, er, g_sr);
+            }
+        }
+    }
+    if constexpr (BWD) {
+        p.g_phi_var[vb] = g_sphi * (kFmSc * kFmSc);
+        if (p.g_r2_mean) p.g_r2_mean[vb] = g_mu * p.r2_sc;
+        if (p.g_r2_var) p.g_r2_var[vb] = g_sr * (p.r2_sc * p.r2_sc);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// PDFF_uncertainty (IDEAL_model.py:628-706): weighted LS with Sigma_e = V_e (|Wp (P0 Wm)|_e^2 + |S_e|^2)
+// -------------------------------------------------------------------------------------------------------------
+struct PdffUncParams {
+    const float *acqs, *phi_mean, *phi_var, *r2_mean, *r2_var, *tab;   // r2_* NULL = rem_R2
+    float *rho, *cov;                                                  // (nb,2,nv,2), (nb,4,nv)
+    int nb, ne, nv;
+    float r2_sc;
+};
+
+template <int NE> __global__ void __launch_bounds__(kThreads) pdff_unc_kernel(const PdffUncParams p) {
+    __shared__ SampleTab<NE> T;
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t vb = static_cast<size_t>(b) * nv + v;
+    const float phi_t = p.phi_mean[vb];
+    const bool r2 = p.r2_mean != nullptr;
+    const float r2map = r2 ? p.r2_mean[vb] : 0.f;
+    const float s_phi = p.phi_var[vb] * (kFmSc * kFmSc);
+    const float mu = r2map * p.r2_sc, s_r = r2 ? p.r2_var[vb] * (p.r2_sc * p.r2_sc) : 0.f;
+    Mod<float> m[NE];
+    cx<float> q_w = czero<float>(), q_f = czero<float>();          // M^+ Wm
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            m[e] = modulator(T, e, phi_t, r2map, 0.f);
+            const cx<float> wm{m[e].dinv * m[e].c, -m[e].dinv * m[e].s};
+            cmac(q_w, T.r[e].pw_re, T.r[e].pw_im, wm);
+            cmac(q_f, T.r[e].pf_re, T.r[e].pf_im, wm);
+        }
+    }
+    // normal equations of the weighted fit: G = M^H W M (Hermitian 2x2), rhs = M^H W y
+    float g00 = 0.f, g11 = 0.f;
+    cx<float> g01 = czero<float>(), r0 = czero<float>(), r1 = czero<float>();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const float te = T.r[e].te, k = kTwoPi * te;
+            float V = 1.0f - __expf(-k * k * s_phi);
+            if (r2) V += __expf(te * mu) * te * te * s_r;
+            const cx<float> wm{m[e].dinv * m[e].c, -m[e].dinv * m[e].s};
+            const cx<float> pw = caffine(q_w, T.r[e].c_re, T.r[e].c_im, q_f);          // (M M^+ Wm)_e
+            const cx<float> res{wm.re - pw.re, wm.im - pw.im};                          // (P0 Wm)_e
+            const cx<float> g = remod(m[e], res);                                       // Wp_e (P0 Wm)_e
+            const float2 s2 = reinterpret_cast<const float2 *>(p.acqs)[(static_cast<size_t>(b) * ne + e) * nv + v];
+            const float sig = V * (g.re * g.re + g.im * g.im) + V * (s2.x * s2.x + s2.y * s2.y);
+            const float w = sig != 0.f ? 1.0f / sig : 0.f;
+            const cx<float> y = demod(m[e], cx<float>{s2.x, s2.y});
+            const float cr = T.r[e].c_re, ci = T.r[e].c_im;
+            g00 += w;
+            g01.re = fmaf(w, cr, g01.re);
+            g01.im = fmaf(w, ci, g01.im);
+            g11 = fmaf(w, cr * cr + ci * ci, g11);
+            r0.re = fmaf(w, y.re, r0.re);
+            r0.im = fmaf(w, y.im, r0.im);
+            r1.re = fmaf(w, cr * y.re + ci * y.im, r1.re);                               // conj(c) y
+            r1.im = fmaf(w, cr * y.im - ci * y.re, r1.im);
+        }
+    }
+    // C = G^-1 = 1/det [[g11, -g01], [-conj(g01), g00]]
+    const float det = g00 * g11 - (g01.re * g01.re + g01.im * g01.im);
+    const float id = 1.0f / det;
+    const float c00 = g11 * id, c11 = g00 * id;
+    const cx<float> c01{-g01.re * id, -g01.im * id};
+    const cx<float> rho_w{c00 * r0.re + (c01.re * r1.re - c01.im * r1.im), c00 * r0.im + (c01.re * r1.im + c01.im * r1.re)};
+    const cx<float> rho_f{(c01.re * r0.re + c01.im * r0.im) + c11 * r1.re, (c01.re * r0.im - c01.im * r0.re) + c11 * r1.im};
+    const float inv = 1.0f / kRhoSc, inv2 = 1.0f / (kRhoSc * kRhoSc);
+    reinterpret_cast<float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 0) * nv + v] = make_float2(rho_w.re * inv, rho_w.im * inv);
+    reinterpret_cast<float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 1) * nv + v] = make_float2(rho_f.re * inv, rho_f.im * inv);
+    const float a01 = sqrtf(c01.re * c01.re + c01.im * c01.im);
+    p.cov[(static_cast<size_t>(b) * 4 + 0) * nv + v] = fabsf(c00) * inv2;
+    p.cov[(static_cast<size_t>(b) * 4 + 1) * nv + v] = a01 * inv2;
+    p.cov[(static_cast<size_t>(b) * 4 + 2) * nv + v] = a01 * inv2;
+    p.cov[(static_cast<size_t>(b) * 4 + 3) * nv + v] = fabsf(c11) * inv2;
+}
+
+// PDFF extraction (ROI-analysis.py:301-306,344-354; gen_LDM_dataset.py:217-218): mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|),
+// 2 magnitude-discriminated; NaN (0/0) -> 0
+__global__ void pdff_extract_kernel(const float *__restrict__ rho, int nb, int nv, int mode, float *__restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (v >= nv) return;
+    const float2 w = reinterpret_cast<const float2 *>(rho)[(static_cast<size_t>(b) * 2 + 0) * nv + v];
+    const float2 f = reinterpret_cast<const float2 *>(rho)[(static_cast<size_t>(b) * 2 + 1) * nv + v];
+    const float wa = sqrtf(w.x * w.x + w.y * w.y), fa = sqrtf(f.x * f.x + f.y * f.y);
+    float r;
+    if (mode == 1) {
+        r = fa / (wa + fa);
+    } else {
+        const float wf = sqrtf((w.x + f.x) * (w.x + f.x) + (w.y + f.y) * (w.y + f.y));
+        r = (mode == 0 || fa >= wa) ? fa / wf : 1.0f - wa / wf;
+    }
+    out[static_cast<size_t>(b) * nv + v] = (isnan(r) || isinf(r)) ? 0.f : r;
+}
+
+static int check_nv(const char *fn, int nb, int ne, int nv, int min_ne) {
+    IG_REQUIRE(nb > 0 && nv > 0 && nb <= 65535, IG_E_ARG, "%s: nb=%d (1..65535), nv=%d", fn, nb, nv);
+    IG_REQUIRE(ne >= min_ne && ne <= IG_MAX_NE, IG_E_NE, "%s: ne=%d outside [%d, %d]", fn, ne, min_ne, IG_MAX_NE);
+    return 0;
+}
+
+}  // namespace ig
+
+using namespace ig;
+
+extern "C" int ig_eigenvals(const float *x_d, long n, float *xy_d, float *ratio_d, void *stream) {
+    IG_REQUIRE(x_d && xy_d && ratio_d && n > 0, IG_E_ARG, "ig_eigenvals: null pointer or n <= 0");
+    eigenvals_kernel<<<static_cast<unsigned>((n + kThreads - 1) / kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x_d, n, xy_d, ratio_d);
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ig_eigenvals_bwd(const float *x_d, long n, const float *g_xy_d, const float *g_ratio_d, float *gx_d, void *stream) {
+    IG_REQUIRE(x_d && gx_d && n > 0, IG_E_ARG, "ig_eigenvals_bwd: null pointer or n <= 0");
+    eigenvals_bwd_kernel<<<static_cast<unsigned>((n + kThreads - 1) / kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x_d, n, g_xy_d, g_ratio_d, gx_d);
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ig_cse_mag_fwd(const float *mag_d, const float *r2_d, const float *r2nu_d, const float *tab_d, int nb, int ne, int nv, float r2_sc,
+                              float *rho_d, float *fit_d, float *demod_d, float *ls_d, float *unc_d, void *stream) {
+    IG_REQUIRE(mag_d && r2_d && tab_d, IG_E_ARG, "ig_cse_mag_fwd: null pointer");
+    if (int rc = check_nv("ig_cse_mag_fwd", nb, ne, nv, 3)) return rc;
+    CseParams p{};
+    p.mag = mag_d; p.r2 = r2_d; p.r2nu = r2nu_d; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    p.rho = rho_d; p.fit = fit_d; p.demod = demod_d; p.ls = ls_d; p.unc = unc_d;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        cse_mag_kernel<NE, false><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+extern "C" int ig_cse_mag_bwd(const float *mag_d, const float *r2_d, const float *r2nu_d, const float *tab_d, int nb, int ne, int nv, float r2_sc,
+                              const float *g_rho_d, const float *g_fit_d, const float *g_demod_d, const float *g_ls_d, const float *g_unc_d,
+                              float *g_mag_d, float *g_r2_d, float *g_r2nu_d, void *stream) {
+    IG_REQUIRE(mag_d && r2_d && tab_d && (g_mag_d || g_r2_d || g_r2nu_d), IG_E_ARG, "ig_cse_mag_bwd: null pointer");
+    if (int rc = check_nv("ig_cse_mag_bwd", nb, ne, nv, 3)) return rc;
+    CseParams p{};
+    p.mag = mag_d; p.r2 = r2_d; p.r2nu = r2nu_d; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    p.g_rho = g_rho_d; p.g_fit = g_fit_d; p.g_demod = g_demod_d; p.g_ls = g_ls_d; p.g_unc = g_unc_d;
+    p.g_mag = g_mag_d; p.g_r2 = g_r2_d; p.g_r2nu = g_r2nu_d;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        cse_mag_kernel<NE, true><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+extern "C" int ig_acq_unc_fwd(const float *rho_d, const float *phi_var_d, const float *r2_mean_d, const float *r2_var_d, const float *tab_d,
+                              int nb, int ne, int nv, float r2_sc, int only_mag, float *out_d, void *stream) {
+    IG_REQUIRE(rho_d && phi_var_d && tab_d && out_d && (!r2_mean_d == !r2_var_d), IG_E_ARG, "ig_acq_unc_fwd: null pointer");
+    if (int rc = check_nv("ig_acq_unc_fwd", nb, ne, nv, 1)) return rc;
+    UncParams p{};
+    p.rho = rho_d; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d; p.out = out_d;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.ch = only_mag ? 1 : 2; p.r2_sc = r2_sc;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        acq_unc_kernel<NE, false><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+extern "C" int ig_acq_unc_bwd(const float *rho_d, const float *phi_var_d, const float *r2_mean_d, const float *r2_var_d, const float *tab_d,
+                              int nb, int ne, int nv, float r2_sc, int only_mag, const float *g_out_d, float *g_phi_var_d, float *g_r2_mean_d,
+                              float *g_r2_var_d, void *stream) {
+    IG_REQUIRE(rho_d && phi_var_d && tab_d && g_out_d && g_phi_var_d && (!r2_mean_d == !r2_var_d), IG_E_ARG, "ig_acq_unc_bwd: null pointer");
+    if (int rc = check_nv("ig_acq_unc_bwd", nb, ne, nv, 1)) return rc;
+    UncParams p{};
+    p.rho = rho_d; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d; p.g_out = g_out_d;
+    p.g_phi_var = g_phi_var_d; p.g_r2_mean = g_r2_mean_d; p.g_r2_var = g_r2_var_d;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.ch = only_mag ? 1 : 2; p.r2_sc = r2_sc;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        acq_unc_kernel<NE, true><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+extern "C" int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const float *phi_var_d, const float *r2_mean_d, const float *r2_var_d,
+                           const float *tab_d, int nb, int ne, int nv, float r2_sc, float *rho_d, float *cov_d, void *stream) {
+    IG_REQUIRE(acqs_d && phi_mean_d && phi_var_d && tab_d && rho_d && cov_d && (!r2_mean_d == !r2_var_d), IG_E_ARG, "ig_pdff_unc: null pointer");
+    if (int rc = check_nv("ig_pdff_unc", nb, ne, nv, 2)) return rc;
+    PdffUncParams p{};
+    p.acqs = acqs_d; p.phi_mean = phi_mean_d; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d;
+    p.rho = rho_d; p.cov = cov_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        pdff_unc_kernel<NE><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
+
+extern "C" int ig_pdff_extract(const float *rho_d, int nb, int nv, int mode, float *out_d, void *stream) {
+    IG_REQUIRE(rho_d && out_d && nb > 0 && nv > 0 && nb <= 65535 && mode >= 0 && mode <= 2, IG_E_ARG, "ig_pdff_extract: bad arguments");
+    pdff_extract_kernel<<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(rho_d, nb, nv, mode, out_d);
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}

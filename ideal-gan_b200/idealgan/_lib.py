@@ -48,6 +48,14 @@ SIGNATURES = {
     "ig_a2a_fwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
     "ig_a2a_bwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
     "ig_a2a_loss": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
+    "ig_eigenvals": (_i, [_fp, _l, _fp, _fp, _fp]),
+    "ig_eigenvals_bwd": (_i, [_fp, _l, _fp, _fp, _fp, _fp]),
+    "ig_cse_mag_fwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "ig_cse_mag_bwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "ig_acq_unc_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _i, _fp, _fp]),
+    "ig_acq_unc_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
+    "ig_pdff_unc": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp]),
+    "ig_pdff_extract": (_i, [_fp, _i, _i, _i, _fp, _fp]),
     "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),
     "ig_ctx_destroy": (None, [C.c_void_p]),
     "ig_a2a_loss_host": (_i, [C.c_void_p, _fp, _fp, _fp, _i, _f, _f, _f, _fp, _fp]),

@@ -211,3 +211,123 @@ def a2a_loss(acqs, pm, tab, r2_sc=200.0, inv_n=None, want_rho=False, want_shat=F
                                  g_pm.data_ptr(), _ptr(rho), _ptr(shat), loss.data_ptr(), scr.data_ptr(), scr.numel(), _stream()),
             "ig_a2a_loss")
     return loss, g_pm, rho, shat
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second tier (ig_tier2.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _plane(t, name, nb, nv):
+    """(nb, 1, H, W, 1)-like tensor -> contiguous (nb, nv) view."""
+    t = _chk(t, name)
+    if t.numel() != nb * nv:
+        raise ValueError(f"{name}: expected {nb} x {nv} values, got shape {tuple(t.shape)}")
+    return t.reshape(nb, nv)
+
+
+def eigenvals_fwd(X):
+    X = _chk(X, "X")
+    if X.shape[-1] != 3:
+        raise ValueError(f"eigenvals: last axis must hold (a, b, c), got {tuple(X.shape)}")
+    n = X.numel() // 3
+    xy = torch.empty(X.shape[:-1] + (2,), dtype=torch.float32, device=X.device)
+    ratio = torch.empty(X.shape[:-1] + (1,), dtype=torch.float32, device=X.device)
+    L.check(L.load().ig_eigenvals(X.data_ptr(), n, xy.data_ptr(), ratio.data_ptr(), _stream()), "ig_eigenvals")
+    return xy, ratio
+
+
+def eigenvals_bwd(X, g_xy, g_ratio):
+    X = _chk(X, "X")
+    gX = torch.empty_like(X)
+    g_xy = None if g_xy is None else _chk(g_xy, "grad xy")
+    g_ratio = None if g_ratio is None else _chk(g_ratio, "grad ratio")
+    L.check(L.load().ig_eigenvals_bwd(X.data_ptr(), X.numel() // 3, _ptr(g_xy), _ptr(g_ratio), gX.data_ptr(), _stream()), "ig_eigenvals_bwd")
+    return gX
+
+
+def cse_mag_fwd(mag, r2, tab, r2_sc=200.0, r2nu=None):
+    mag = _chk(mag, "acqs", 5)
+    nb, ne, H, W, ch = mag.shape
+    if ch != 1:
+        raise ValueError(f"CSE_mag takes magnitudes (nb, ne, H, W, 1), got {tuple(mag.shape)}")
+    nv = H * W
+    r2 = _plane(r2, "out_maps", nb, nv)
+    r2nu = None if r2nu is None else _plane(r2nu, "out_maps.nu", nb, nv)
+    new = lambda c: torch.empty((nb, c, H, W, 1), dtype=torch.float32, device=mag.device)   # noqa: E731
+    rho, fit, demod, ls, unc = new(2), new(ne), new(ne), new(3), new(1)
+    L.check(L.load().ig_cse_mag_fwd(mag.data_ptr(), r2.data_ptr(), _ptr(r2nu), tab.data_ptr(), nb, ne, nv, float(r2_sc), rho.data_ptr(),
+                                    fit.data_ptr(), demod.data_ptr(), ls.data_ptr(), unc.data_ptr(), _stream()), "ig_cse_mag_fwd")
+    return rho, fit, demod, ls, unc
+
+
+def cse_mag_bwd(mag, r2, tab, grads, r2_sc=200.0, r2nu=None):
+    mag = _chk(mag, "acqs", 5)
+    nb, ne, H, W, _ = mag.shape
+    nv = H * W
+    r2v = _plane(r2, "out_maps", nb, nv)
+    r2nuv = None if r2nu is None else _plane(r2nu, "out_maps.nu", nb, nv)
+    gs = [None if g is None else _chk(g, "upstream") for g in grads]
+    g_mag, g_r2 = torch.empty_like(mag), torch.empty_like(r2v)
+    g_nu = None if r2nu is None else torch.empty_like(r2nuv)
+    L.check(L.load().ig_cse_mag_bwd(mag.data_ptr(), r2v.data_ptr(), _ptr(r2nuv), tab.data_ptr(), nb, ne, nv, float(r2_sc), *[_ptr(g) for g in gs],
+                                    g_mag.data_ptr(), g_r2.data_ptr(), _ptr(g_nu), _stream()), "ig_cse_mag_bwd")
+    return g_mag, g_r2.reshape(r2.shape), None if g_nu is None else g_nu.reshape(r2nu.shape)
+
+
+def acq_unc_fwd(rho, phi_var, r2_mean, r2_var, tab, ne, r2_sc=200.0, only_mag=False):
+    rho = _chk(rho, "rho_maps", 5)
+    nb, rows, H, W, ch = rho.shape
+    if rows < 2 or ch != 2:
+        raise ValueError(f"rho_maps must be (nb, >=2, H, W, 2), got {tuple(rho.shape)}")
+    rho = rho[:, :2].contiguous()
+    nv = H * W
+    pv = _plane(phi_var, "phi variance", nb, nv)
+    rm = None if r2_mean is None else _plane(r2_mean, "R2* mean", nb, nv)
+    rv = None if r2_var is None else _plane(r2_var, "R2* variance", nb, nv)
+    out = torch.empty((nb, ne, H, W, 1 if only_mag else 2), dtype=torch.float32, device=rho.device)
+    L.check(L.load().ig_acq_unc_fwd(rho.data_ptr(), pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv, float(r2_sc), int(only_mag),
+                                    out.data_ptr(), _stream()), "ig_acq_unc_fwd")
+    return out
+
+
+def acq_unc_bwd(rho, phi_var, r2_mean, r2_var, tab, ne, g_out, r2_sc=200.0, only_mag=False):
+    rho = _chk(rho, "rho_maps", 5)[:, :2].contiguous()
+    nb, _, H, W, _ = rho.shape
+    nv = H * W
+    pv = _plane(phi_var, "phi variance", nb, nv)
+    rm = None if r2_mean is None else _plane(r2_mean, "R2* mean", nb, nv)
+    rv = None if r2_var is None else _plane(r2_var, "R2* variance", nb, nv)
+    g_out = _chk(g_out, "upstream")
+    g_pv = torch.empty_like(pv)
+    g_rm = None if rm is None else torch.empty_like(rm)
+    g_rv = None if rv is None else torch.empty_like(rv)
+    L.check(L.load().ig_acq_unc_bwd(rho.data_ptr(), pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv, float(r2_sc), int(only_mag),
+                                    g_out.data_ptr(), g_pv.data_ptr(), _ptr(g_rm), _ptr(g_rv), _stream()), "ig_acq_unc_bwd")
+    return (g_pv.reshape(phi_var.shape), None if g_rm is None else g_rm.reshape(r2_mean.shape),
+            None if g_rv is None else g_rv.reshape(r2_var.shape))
+
+
+def pdff_unc(acqs, phi_mean, phi_var, r2_mean, r2_var, tab, r2_sc=200.0):
+    acqs, nb, ne, H, W = _acq_dims(acqs, False)
+    nv = H * W
+    pm, pv = _plane(phi_mean, "phi mean", nb, nv), _plane(phi_var, "phi variance", nb, nv)
+    rm = None if r2_mean is None else _plane(r2_mean, "R2* mean", nb, nv)
+    rv = None if r2_var is None else _plane(r2_var, "R2* variance", nb, nv)
+    rho = torch.empty((nb, 2, H, W, 2), dtype=torch.float32, device=acqs.device)
+    cov = torch.empty((nb, 4, H, W, 1), dtype=torch.float32, device=acqs.device)
+    L.check(L.load().ig_pdff_unc(acqs.data_ptr(), pm.data_ptr(), pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv, float(r2_sc),
+                                 rho.data_ptr(), cov.data_ptr(), _stream()), "ig_pdff_unc")
+    return rho, cov
+
+
+PDFF_MODES = {"complex_sum": 0, "mag_sum": 1, "mag_disc": 2}
+
+
+def pdff_extract(rho, mode="complex_sum"):
+    rho = _chk(rho, "rho", 5)
+    nb, rows, H, W, ch = rho.shape
+    if rows < 2 or ch != 2:
+        raise ValueError(f"rho must be (nb, >=2, H, W, 2), got {tuple(rho.shape)}")
+    rho = rho[:, :2].contiguous()
+    out = torch.empty((nb, H, W), dtype=torch.float32, device=rho.device)
+    L.check(L.load().ig_pdff_extract(rho.data_ptr(), nb, H * W, PDFF_MODES[mode], out.data_ptr(), _stream()), "ig_pdff_extract")
+    return out

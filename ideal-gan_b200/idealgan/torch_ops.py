@@ -1,0 +1,240 @@
+"""torch.autograd bindings over the C ABI (idealgan.ops): the differentiable operators the `wflib` drop-in is
+built from.  TF's autodiff through ~25 ops per operator in the reference becomes one forward
+and one adjoint kernel launch here.  The TensorFlow binding (tf_ops.py) wraps these same functions.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _tables(te, field, device):
+    """te: (nb, ne[, 1]) tensor/array on any device -> (table on `device`, ne).  No gradient: echo times are data."""
+    if not isinstance(te, torch.Tensor):
+        te = torch.as_tensor(te, dtype=torch.float32)
+    te = te.detach().to(device=device, dtype=torch.float32)
+    if te.dim() == 3:
+        te = te[:, :, 0]
+    if te.dim() != 2:
+        raise ValueError(f"te must be (nb, ne, 1) or (nb, ne), got {tuple(te.shape)}")
+    return ops.gen_tables(te.contiguous(), field), te.shape[1]
+
+
+def _check_batch(te_nb, nb):
+    if te_nb != nb:
+        raise ValueError(f"te has {te_nb} rows for a batch of {nb} (one echo train per sample)")
+
+
+class _IdealForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, tab, model, ne, r2_sc, flags):
+        maps = maps.contiguous()
+        ctx.save_for_backward(maps, tab)
+        ctx.cfg = (model, ne, r2_sc, flags)
+        return ops.ideal_fwd(model, maps, tab, ne, r2_sc, flags)
+
+    @staticmethod
+    def backward(ctx, gout):
+        maps, tab = ctx.saved_tensors
+        model, ne, r2_sc, flags = ctx.cfg
+        return ops.ideal_bwd(model, maps, tab, ne, gout.contiguous(), r2_sc, flags), None, None, None, None, None
+
+
+def ideal_forward(model, maps, te, field=1.5, r2_sc=200.0, flags=0):
+    """Forward signal model (IDEAL_model / IDEAL_mag / IDEAL_mag_phase) with its adjoint registered."""
+    tab, ne = _tables(te, field, maps.device)
+    _check_batch(tab.shape[0], maps.shape[0])
+    return _IdealForward.apply(maps, tab, model, ne, float(r2_sc), int(flags))
+
+
+class _GetRho(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acqs, pm, tab, r2_sc, flags, want_demod):
+        acqs, pm = acqs.contiguous(), pm.contiguous()
+        ctx.save_for_backward(acqs, pm, tab)
+        ctx.cfg = (r2_sc, flags)
+        rho, demod = ops.get_rho_fwd(acqs, pm, tab, r2_sc, flags, want_demod)
+        if demod is None:
+            demod = acqs.new_empty(0)
+            ctx.mark_non_differentiable(demod)
+        return rho, demod
+
+    @staticmethod
+    def backward(ctx, g_rho, g_demod):
+        acqs, pm, tab = ctx.saved_tensors
+        r2_sc, flags = ctx.cfg
+        if flags & L.F_PHASE_CONSTRAINT:
+            raise NotImplementedError("get_rho(phase_constraint=True) is an inference-only operator in the reference's "
+                                      "callers (ROI-analysis.py:217-228); no adjoint kernel is provided")
+        g_demod = None if g_demod is None or g_demod.numel() == 0 else g_demod.contiguous()
+        g_rho = None if g_rho is None else g_rho.contiguous()
+        g_acqs, g_pm = ops.get_rho_bwd(acqs, pm, tab, g_rho, g_demod, r2_sc, flags, need_acqs=ctx.needs_input_grad[0])
+        return g_acqs, g_pm, None, None, None, None
+
+
+def get_rho(acqs, pm, te, field=1.5, r2_sc=200.0, flags=0, want_demod=False):
+    flat = bool(flags & L.F_FLAT)
+    tab, ne = _tables(te, field, acqs.device)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    if ne != (acqs.shape[-1] // 2 if flat else acqs.shape[1]):
+        raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[-1] // 2 if flat else acqs.shape[1]}")
+    rho, demod = _GetRho.apply(acqs, pm, tab, float(r2_sc), int(flags), bool(want_demod))
+    return (rho, demod) if want_demod else rho
+
+
+class _AcqToAcq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acqs, pm, tab, r2_sc, flags):
+        acqs, pm = acqs.contiguous(), pm.contiguous()
+        ctx.save_for_backward(acqs, pm, tab)
+        ctx.cfg = (r2_sc, flags)
+        return ops.a2a_fwd(acqs, pm, tab, r2_sc, flags, want_rho=True)
+
+    @staticmethod
+    def backward(ctx, g_rho, g_shat):
+        acqs, pm, tab = ctx.saved_tensors
+        r2_sc, flags = ctx.cfg
+        g_rho = None if g_rho is None else g_rho.contiguous()
+        g_shat = None if g_shat is None else g_shat.contiguous()
+        g_acqs, g_pm = ops.a2a_bwd(acqs, pm, tab, g_rho, g_shat, r2_sc, flags, need_acqs=ctx.needs_input_grad[0])
+        return g_acqs, g_pm, None, None, None
+
+
+def acq_to_acq(acqs, pm, te, field=1.5, r2_sc=200.0, only_mag=False):
+    """(rho_hat / rho_sc, S_hat) -- or |S_hat| with only_mag -- differentiable in acqs and pm."""
+    tab, ne = _tables(te, field, acqs.device)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    if ne != acqs.shape[1]:
+        raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[1]}")
+    return _AcqToAcq.apply(acqs, pm, tab, float(r2_sc), L.F_ONLY_MAG if only_mag else 0)
+
+
+class _A2ALoss(torch.autograd.Function):
+    """Fused config-2 objective: the forward pass already produces d loss / d pm, backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, acqs, pm, tab, r2_sc, inv_n):
+        loss, g_pm, _, _ = ops.a2a_loss(acqs.contiguous(), pm.contiguous(), tab, r2_sc, inv_n)
+        if pm.shape[1] != 1:
+            full = torch.zeros_like(pm)
+            full[:, :1] = g_pm
+            g_pm = full
+        ctx.save_for_backward(g_pm)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (g_pm,) = ctx.saved_tensors
+        return None, g_pm * g, None, None, None
+
+
+def physics_loss_a2a(acqs, pm, te, field=1.5, r2_sc=200.0, inv_n=None):
+    """mean((A - where(A != 0, acq_to_acq(A, pm), 0))^2) as one kernel (train-IDEAL-unsup.py:214-218,236,255).
+    Differentiable in pm only (A is data).  inv_n: 1 / (elements of the global batch) for sharded batches."""
+    tab, ne = _tables(te, field, acqs.device)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    inv_n = 1.0 / acqs.numel() if inv_n is None else float(inv_n)
+    return _A2ALoss.apply(acqs, pm, tab, float(r2_sc), inv_n)
+
+
+class _IdealLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, maps, acqs, tab, model, r2_sc, flags, inv_n):
+        loss, gmaps, _ = ops.ideal_loss(model, maps.contiguous(), acqs.contiguous(), tab, r2_sc, flags, inv_n)
+        ctx.save_for_backward(gmaps)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gmaps,) = ctx.saved_tensors
+        return gmaps * g, None, None, None, None, None, None
+
+
+def physics_loss_forward(model, maps, acqs, te, field=1.5, r2_sc=200.0, flags=0, inv_n=None):
+    """mean((A - where(A != 0, forward_model(maps), 0))^2) as one kernel (train-IDEAL-single.py:154-157,175)."""
+    tab, ne = _tables(te, field, maps.device)
+    _check_batch(tab.shape[0], maps.shape[0])
+    if ne != acqs.shape[1]:
+        raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[1]}")
+    inv_n = 1.0 / acqs.numel() if inv_n is None else float(inv_n)
+    return _IdealLoss.apply(maps, acqs, tab, model, float(r2_sc), int(flags), inv_n)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second tier
+# ---------------------------------------------------------------------------------------------------------------
+class _Eigenvals(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X):
+        X = X.contiguous()
+        ctx.save_for_backward(X)
+        return ops.eigenvals_fwd(X)
+
+    @staticmethod
+    def backward(ctx, g_xy, g_ratio):
+        (X,) = ctx.saved_tensors
+        return ops.eigenvals_bwd(X, g_xy, g_ratio)
+
+
+def eigenvals(X):
+    return _Eigenvals.apply(X)
+
+
+class _CseMag(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mag, r2, r2nu, tab, r2_sc):
+        mag, r2 = mag.contiguous(), r2.contiguous()
+        has_nu = r2nu is not None
+        ctx.save_for_backward(mag, r2, tab, r2nu.contiguous() if has_nu else tab)
+        ctx.cfg = (r2_sc, has_nu)
+        return ops.cse_mag_fwd(mag, r2, tab, r2_sc, r2nu)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        mag, r2, tab, nu = ctx.saved_tensors
+        r2_sc, has_nu = ctx.cfg
+        g_mag, g_r2, g_nu = ops.cse_mag_bwd(mag, r2, tab, grads, r2_sc, nu if has_nu else None)
+        return g_mag, g_r2, g_nu, None, None
+
+
+def cse_mag(mag, r2, te, field=1.5, r2_sc=200.0, r2nu=None):
+    """(rho/rho_sc, S_hat, demodulated y, abc/rho_sc^2, rank-1 ratio), differentiable in mag, r2 (and r2nu)."""
+    tab, ne = _tables(te, field, mag.device)
+    _check_batch(tab.shape[0], mag.shape[0])
+    if ne != mag.shape[1]:
+        raise ValueError(f"te has {ne} echoes, acquisitions have {mag.shape[1]}")
+    return _CseMag.apply(mag, r2, r2nu, tab, float(r2_sc))
+
+
+class _AcqUnc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rho, phi_var, r2_mean, r2_var, tab, ne, r2_sc, only_mag):
+        rem = r2_mean is None
+        ctx.save_for_backward(rho, phi_var, tab, *( () if rem else (r2_mean, r2_var)))
+        ctx.cfg = (ne, r2_sc, only_mag, rem)
+        return ops.acq_unc_fwd(rho, phi_var, r2_mean, r2_var, tab, ne, r2_sc, only_mag)
+
+    @staticmethod
+    def backward(ctx, g):
+        ne, r2_sc, only_mag, rem = ctx.cfg
+        saved = ctx.saved_tensors
+        rho, phi_var, tab = saved[:3]
+        r2_mean, r2_var = (None, None) if rem else saved[3:]
+        g_pv, g_rm, g_rv = ops.acq_unc_bwd(rho, phi_var, r2_mean, r2_var, tab, ne, g.contiguous(), r2_sc, only_mag)
+        return None, g_pv, g_rm, g_rv, None, None, None, None
+
+
+def acq_uncertainty(rho, phi_var, r2_mean, r2_var, te, field=1.5, r2_sc=200.0, only_mag=False):
+    """Var_e = V_e |M rho|^2; differentiable in the three moment maps (rho is a constant, as in its callers:
+    train-IDEAL-unsup.py:222 passes tf.stop_gradient(A2B_WF))."""
+    tab, ne = _tables(te, field, rho.device)
+    _check_batch(tab.shape[0], rho.shape[0])
+    return _AcqUnc.apply(rho.detach(), phi_var, r2_mean, r2_var, tab, ne, float(r2_sc), bool(only_mag))
+
+
+def pdff_uncertainty(acqs, phi_mean, phi_var, r2_mean, r2_var, te, r2_sc=200.0):
+    """Inference-only weighted LS (no adjoint: its only callers are evaluation scripts, ROI-analysis.py:240-244)."""
+    tab, ne = _tables(te, 1.5, acqs.device)          # the reference fixes 1.5 T here (IDEAL_model.py:634)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    with torch.no_grad():
+        return ops.pdff_unc(acqs.detach(), phi_mean, phi_var, r2_mean, r2_var, tab, r2_sc)

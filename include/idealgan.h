@@ -126,6 +126,31 @@ int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const f
                 float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
                 size_t scratch_bytes, void *stream);
 
+/* ---- second tier: magnitude fit, uncertainty propagation, PDFF (IDEAL_model.py:100-138,314-401,628-767) ---- */
+/* eigenvals: x_d (n, 3) = (a, b, c) -> xy_d (n, 2), ratio_d (n); adjoint with optional upstreams */
+int ig_eigenvals(const float *x_d, long n, float *xy_d, float *ratio_d, void *stream);
+int ig_eigenvals_bwd(const float *x_d, long n, const float *g_xy_d, const float *g_ratio_d, float *gx_d, void *stream);
+/* CSE_mag: mag_d (nb, ne, nv) magnitudes, r2_d (nb, nv) R2* / r2_sc, r2nu_d optional second R2* map (R2_prob).
+ * Outputs (each optional): rho (nb,2,nv) / rho_sc, fit (nb,ne,nv), demod (nb,ne,nv), ls (nb,3,nv) / rho_sc^2, unc (nb,nv). */
+int ig_cse_mag_fwd(const float *mag_d, const float *r2_d, const float *r2nu_d, const float *tab_d, int nb, int ne, int nv,
+                   float r2_sc, float *rho_d, float *fit_d, float *demod_d, float *ls_d, float *unc_d, void *stream);
+int ig_cse_mag_bwd(const float *mag_d, const float *r2_d, const float *r2nu_d, const float *tab_d, int nb, int ne, int nv,
+                   float r2_sc, const float *g_rho_d, const float *g_fit_d, const float *g_demod_d, const float *g_ls_d,
+                   const float *g_unc_d, float *g_mag_d, float *g_r2_d, float *g_r2nu_d, void *stream);
+/* acq_uncertainty: rho_d (nb,2,nv,2), phi_var_d / r2_mean_d / r2_var_d (nb,nv) in map units (r2_* NULL = rem_R2)
+ * -> out_d (nb, ne, nv, only_mag ? 1 : 2); adjoint w.r.t. the three moment maps (rho is a constant for its callers) */
+int ig_acq_unc_fwd(const float *rho_d, const float *phi_var_d, const float *r2_mean_d, const float *r2_var_d,
+                   const float *tab_d, int nb, int ne, int nv, float r2_sc, int only_mag, float *out_d, void *stream);
+int ig_acq_unc_bwd(const float *rho_d, const float *phi_var_d, const float *r2_mean_d, const float *r2_var_d,
+                   const float *tab_d, int nb, int ne, int nv, float r2_sc, int only_mag, const float *g_out_d,
+                   float *g_phi_var_d, float *g_r2_mean_d, float *g_r2_var_d, void *stream);
+/* PDFF_uncertainty: acqs_d (nb,ne,nv,2) + moment maps (nb,nv) -> rho_d (nb,2,nv,2), cov_d (nb,4,nv) = |C| / rho_sc^2 */
+int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const float *phi_var_d, const float *r2_mean_d,
+                const float *r2_var_d, const float *tab_d, int nb, int ne, int nv, float r2_sc, float *rho_d, float *cov_d,
+                void *stream);
+/* PDFF maps from rho (nb,2,nv,2): mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|), 2 magnitude-discriminated; 0/0 -> 0 */
+int ig_pdff_extract(const float *rho_d, int nb, int nv, int mode, float *out_d, void *stream);
+
 /* ---- host-buffer pipeline (the call timed as `e2e` by bench.py) -------------------------------- */
 /* A context owns device staging buffers and streams on `device`; chunks of `chunk_nb` samples are copied
  * host->device, processed and copied back with copy/compute overlap.  Host buffers should be pinned. */
