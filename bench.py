@@ -327,7 +327,7 @@ def run_ours(args):
                     "api": f"ig_a2a_loss_host (3-slot H2D/compute/D2H pipeline, chunks of {args.chunk} slices)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "a2a_loss_kernel<6, pk, false>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "a2a_loss_tma_kernel<6, 2, 3, true>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VOXEL * NB * nv,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": cpu_baseline,

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Per-kernel timing of every entry point at the BASELINE configs, with the algorithmic bytes per voxel
+and the resulting fraction of the measured HBM roofline.  Writes one JSON document to stdout.
+
+    python tools/kernel_bench.py [--reps 20] > profiles/kernels_rNN.json
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "ideal-gan_b200")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from idealgan import _lib as L  # noqa: E402
+from idealgan import ops, synth  # noqa: E402
+
+
+def timeit(fn, reps):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    rows = []
+
+    def add(name, cfg, nb, nv, ne, bytes_per_voxel, fn):
+        med, best = timeit(fn, args.reps)
+        gbs = bytes_per_voxel * nb * nv / (med * 1e-3) / 1e9
+        rows.append({"kernel": name, "config": cfg, "nb": nb, "nv": nv, "ne": ne, "bytes_per_voxel": bytes_per_voxel,
+                     "ms_median": med, "ms_best": best, "GBps": gbs, "frac_of_measured_hbm": gbs / peak,
+                     "voxel_echoes_per_s": nb * nv * ne / (med * 1e-3)})
+
+    def make(nb, H, W, ne, bip=False, te_random=False):
+        rng = np.random.default_rng(1234)
+        mask = torch.from_numpy(synth.disc_mask(H, W).astype(np.float32)).to(dev)[None, None, :, :, None]
+        maps = torch.empty((nb, 4 if bip else 3, H, W, 2), device=dev)
+        maps[:, :2] = torch.rand((nb, 2, H, W, 2), device=dev, generator=g) - 0.5
+        maps[:, 2, :, :, 0] = 2 * torch.rand((nb, H, W), device=dev, generator=g) - 1
+        maps[:, 2, :, :, 1] = torch.rand((nb, H, W), device=dev, generator=g)
+        if bip:
+            maps[:, 3] = 0.5 * torch.rand((nb, H, W, 2), device=dev, generator=g) - 0.25
+        maps *= mask
+        te = torch.from_numpy(synth.te_random(nb, ne, rng) if te_random else synth.te_orig(nb, ne)).to(dev)
+        tab = ops.gen_tables(te, 1.5)
+        sig = ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne)
+        acqs = torch.where(sig != 0, sig + 0.02 * torch.randn(sig.shape, device=dev, generator=g), torch.zeros_like(sig)).contiguous()
+        return maps, te, tab, acqs
+
+    # C2-sized tensors: 64 x 384 x 384 x 6
+    nb, H, W, ne = 64, 384, 384, 6
+    nv = H * W
+    maps, te, tab, acqs = make(nb, H, W, ne)
+    pm = (maps[:, 2:3] * 0.95).contiguous()
+    up = torch.randn_like(acqs)
+    up_rho = torch.randn((nb, 2, H, W, 2), device=dev)
+    add("ig_gen_tables", "C2", nb, nv, ne, 0, lambda: ops.gen_tables(te, 1.5))
+    add("ig_ideal_fwd[wfpm]", "C1/C3 forward", nb, nv, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
+    add("ig_ideal_bwd[wfpm]", "adjoint", nb, nv, ne, 8 * ne + 24 + 24, lambda: ops.ideal_bwd(L.MODEL_WFPM, maps, tab, ne, up))
+    add("ig_ideal_loss[wfpm]", "fused fwd+mask+MSE+bwd", nb, nv, ne, 8 * ne + 24 + 24, lambda: ops.ideal_loss(L.MODEL_WFPM, maps, acqs, tab))
+    add("ig_get_rho_fwd", "C1 LS solve", nb, nv, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm, tab))
+    add("ig_get_rho_bwd", "LS solve adjoint (dPM + dS)", nb, nv, ne, 8 * ne + 8 + 16 + 8 * ne + 8,
+        lambda: ops.get_rho_bwd(acqs, pm, tab, up_rho, None))
+    add("ig_a2a_fwd", "acq_to_acq forward (rho + S_hat)", nb, nv, ne, 8 * ne + 8 + 16 + 8 * ne, lambda: ops.a2a_fwd(acqs, pm, tab))
+    add("ig_a2a_bwd", "acq_to_acq adjoint (dPM only)", nb, nv, ne, 8 * ne + 8 + 8 * ne + 8,
+        lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=False))
+    add("ig_a2a_loss", "C2 fused objective (headline)", nb, nv, ne, 8 * ne + 8 + 8, lambda: ops.a2a_loss(acqs, pm, tab))
+    add("ig_a2a_loss[+rho,S_hat]", "C2 fused + materialised outputs", nb, nv, ne, 8 * ne + 8 + 8 + 16 + 8 * ne,
+        lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True))
+    # C4: bipolar mag/phase fused objective
+    mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
+    mp[:, 1] -= 0.25
+    mp *= torch.from_numpy(synth.disc_mask(H, W).astype(np.float32)).to(dev)[None, None, :, :, None]
+    add("ig_ideal_fwd[magpha]", "C4 forward", nb, nv, ne, 32 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_MAGPHA, mp, tab, ne))
+    add("ig_ideal_loss[magpha]", "C4 fused objective", nb, nv, ne, 8 * ne + 32 + 32, lambda: ops.ideal_loss(L.MODEL_MAGPHA, mp, acqs, tab))
+    ff = torch.rand((nb, 3, H, W, 2), device=dev, generator=g)
+    add("ig_ideal_fwd[ffpd]", "C5 forward", nb, nv, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_FFPD, ff, tab, ne))
+    del maps, acqs, up, mp, ff
+    torch.cuda.empty_cache()
+    # C3: 256 x 192 x 192 x 6, per-sample random echo times
+    nb, H, W = 256, 192, 192
+    nv = H * W
+    maps, te, tab, acqs = make(nb, H, W, ne, te_random=True)
+    add("ig_ideal_fwd[wfpm]", "C3 per-sample TEs 256x192x192", nb, nv, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
+    add("ig_get_rho_fwd", "C3", nb, nv, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, maps[:, 2:3].contiguous(), tab))
+    del maps, acqs
+    torch.cuda.empty_cache()
+    # C1: single slice latency
+    maps, te, tab, acqs = make(1, 384, 384, ne)
+    pm1 = maps[:, 2:3].contiguous()
+    add("ig_ideal_fwd[wfpm]", "C1 single slice (latency)", 1, 384 * 384, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
+    add("ig_get_rho_fwd", "C1 single slice (latency)", 1, 384 * 384, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm1, tab))
+    print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
