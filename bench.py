@@ -243,32 +243,35 @@ def run_ours(args):
     final_loss = loss.item()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------------------
-    acqs_h = torch.empty(acqs.shape, dtype=torch.float32).pin_memory()
-    pm_h = torch.empty(pm.shape, dtype=torch.float32).pin_memory()
-    te_h = te2.cpu().pin_memory()
-    acqs_h.copy_(acqs)
-    pm_h.copy_(pm)
-    g_h = torch.empty(g_pm.shape, dtype=torch.float32).pin_memory()
-    l_h = torch.empty(1, dtype=torch.float32).pin_memory()
-    ctx = ctypes.c_void_p()
-    L.check(lib.ig_ctx_create(local, args.chunk, NE, nv, ctypes.byref(ctx)), "ig_ctx_create")
+    e2e_s, e2e_steps, e2e_loss, h2d, d2h = 0.0, 0, None, 0, 0
+    if not args.no_e2e:
+        acqs_h = torch.empty(acqs.shape, dtype=torch.float32).pin_memory()
+        pm_h = torch.empty(pm.shape, dtype=torch.float32).pin_memory()
+        te_h = te2.cpu().pin_memory()
+        acqs_h.copy_(acqs)
+        pm_h.copy_(pm)
+        g_h = torch.empty(g_pm.shape, dtype=torch.float32).pin_memory()
+        l_h = torch.empty(1, dtype=torch.float32).pin_memory()
+        h2d, d2h = int((acqs_h.numel() + pm_h.numel() + te_h.numel()) * 4), int((g_h.numel() + 1) * 4)
+        ctx = ctypes.c_void_p()
+        L.check(lib.ig_ctx_create(local, args.chunk, NE, nv, ctypes.byref(ctx)), "ig_ctx_create")
 
-    def e2e_step():
-        L.check(lib.ig_a2a_loss_host(ctx, acqs_h.data_ptr(), pm_h.data_ptr(), te_h.data_ptr(), NB, FIELD, R2_SC, inv_n, l_h.data_ptr(),
-                                     g_h.data_ptr()), "ig_a2a_loss_host")
+        def e2e_step():
+            L.check(lib.ig_a2a_loss_host(ctx, acqs_h.data_ptr(), pm_h.data_ptr(), te_h.data_ptr(), NB, FIELD, R2_SC, inv_n, l_h.data_ptr(),
+                                         g_h.data_ptr()), "ig_a2a_loss_host")
 
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    for _ in range(3):
-        e2e_step()
-    fence()
-    with clocks:
-        w0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        e2e_steps = max(3, min(args.steps, args.e2e_steps))
+        for _ in range(3):
             e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - w0
-    lib.ig_ctx_destroy(ctx)
-    e2e_loss = l_h.item() * world if world > 1 else l_h.item()
+        fence()
+        with clocks:
+            w0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - w0
+        lib.ig_ctx_destroy(ctx)
+        e2e_loss = l_h.item() * world if world > 1 else l_h.item()
     clocks.close()
 
     # ---- max over ranks ----------------------------------------------------------------------------------
@@ -278,7 +281,7 @@ def run_ours(args):
     ms, kernel_ms, e2e_ms = (float(x) for x in times.cpu())
     units_per_step = NB * nv * NE * world
     value = units_per_step * args.steps / (ms * 1e-3)
-    e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3)
+    e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
 
     if rank == 0:
         peaks = {}
@@ -321,13 +324,14 @@ def run_ours(args):
                        "step": "ig_gen_tables + ig_a2a_loss (fused loss + gradient)" + (" + all_reduce(loss)" if world > 1 else ""),
                        "loss": final_loss, "e2e_loss": e2e_loss},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((acqs_h.numel() + pm_h.numel() + te_h.numel()) * 4),
-                    "d2h_bytes_per_step": int((g_h.numel() + 1) * 4), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+            "e2e": None if not e2e_steps else {
+                    "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "timer": "host perf_counter around the blocking C-ABI call, device synchronised on both sides",
                     "api": f"ig_a2a_loss_host (3-slot H2D/compute/D2H pipeline, chunks of {args.chunk} slices)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "a2a_loss_tma_kernel<6, 2, 3, true>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "a2a_loss_tma_kernel<NE=6, MINB=2, STAGES=3, EXACT, CH=8, MODE=1>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VOXEL * NB * nv,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": cpu_baseline,
@@ -347,6 +351,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="slices per chunk of the host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:

@@ -544,28 +544,31 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
 // has turned the raw echoes into registers.  Loads therefore cost the consumers no registers, no address
 // arithmetic and no long-scoreboard stalls, and up to STAGES tiles per block are in flight to HBM.
 // =================================================================================================
-constexpr int kTileVox = kThreads * 2;                 // voxels per tile (two per consumer thread)
-constexpr int kPlaneBytes = kTileVox * 8;              // one complex plane of a tile
-template <int NE, int STAGES> struct TmaCfg {
+constexpr int kChunkVox = 64;                          // voxels per consumer-warp chunk (two per lane)
+template <int NE, int STAGES, int CH> struct TmaCfg {
+    static constexpr int tile_vox = CH * kChunkVox;                               // voxels per tile = per ring stage
+    static constexpr int plane_bytes = tile_vox * 8;                              // one complex plane of a tile
     static constexpr int tab_bytes = NE * IG_REC_FLOATS * 4;                      // the sample's echo records ride along with the tile
-    static constexpr int stage_bytes = (NE + 1) * kPlaneBytes + ((tab_bytes + 127) / 128) * 128;
+    static constexpr int stage_bytes = (NE + 1) * plane_bytes + ((tab_bytes + 127) / 128) * 128;
     static constexpr int smem_bytes = STAGES * stage_bytes;
 };
 
 // Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
 // cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
-template <int NE, int MINB, int STAGES, bool EXACT> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
+template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ int2 stage_tile[STAGES];             // (sample, first voxel) of the tile in each stage; sample < 0 = end
     __shared__ int chunk_ctr;                       // consumer warps draw 64-voxel chunks of the ring from here
+    using Cfg = TmaCfg<NE, STAGES, CH>;
+    constexpr int kTileVox = Cfg::tile_vox, kPlaneBytes = Cfg::plane_bytes;
     const int nv = p.nv, ne = EXACT ? NE : p.ne;
     const int tiles_ps = (nv + kTileVox - 1) / kTileVox;
     const int total = p.nb * tiles_ps;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kThreads / 32);
+            mbar_init(&empty_bar[s], CH);
         }
         chunk_ctr = 0;
         mbar_fence_init();
@@ -587,24 +590,31 @@ template <int NE, int MINB, int STAGES, bool EXACT> __global__ void __launch_bou
                 const int vs = static_cast<int>((static_cast<unsigned long long>(j) * static_cast<unsigned>(p.tile_stride)) % static_cast<unsigned>(tiles_ps)) * kTileVox;
                 return make_int2(b, vs);
             };
+            // the claim for the next tile is in flight (an L2 atomic, ~1 us under load) while this one is waited for and issued
+            int2 nxt = claim();
+            int ends_left = (kThreads / 32 + CH - 1) / CH;
             for (int it = 0;; ++it) {
                 const int s = it % STAGES;
-                const int2 cur = claim();
+                const int2 cur = nxt;
+                if (cur.x >= 0) nxt = claim();
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
                 stage_tile[s] = cur;
                 if (cur.x < 0) {
-                    mbar_arrive(&full_bar[s]);                 // end marker: completes the phase without data
-                    break;
+                    // end marker: completes the phase without data.  Every consumer warp draws exactly one chunk past
+                    // the data, so enough marker stages are published to cover all of them.
+                    mbar_arrive(&full_bar[s]);
+                    if (--ends_left == 0) break;
+                    continue;
                 }
                 const int b = cur.x, vs = cur.y;
                 const int nvox = (nv - vs < kTileVox) ? nv - vs : kTileVox;
                 const uint32_t bytes = static_cast<uint32_t>(nvox) * 8u;
-                unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
-                mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + TmaCfg<NE, STAGES>::tab_bytes);
+                unsigned char *stage = stage_mem + s * Cfg::stage_bytes;
+                mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + Cfg::tab_bytes);
                 const float *src = p.acqs + (static_cast<size_t>(b) * ne * nv + vs) * 2;
                 for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + e * plane_stride, bytes, &full_bar[s]);
                 bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
-                bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, TmaCfg<NE, STAGES>::tab_bytes, &full_bar[s]);
+                bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, Cfg::tab_bytes, &full_bar[s]);
             }
         }
     } else {
@@ -612,7 +622,7 @@ template <int NE, int MINB, int STAGES, bool EXACT> __global__ void __launch_bou
         // Warps are decoupled: each draws the next 64-voxel chunk (1/8 of a tile) from a shared counter, so a warp
         // that lands on background (skipped in ~40 instructions) immediately moves on instead of idling until the
         // tissue warps of its tile finish.  A stage returns to the producer when its 8 chunks have been released.
-        constexpr int kChunks = kThreads / 32;
+        constexpr int kChunks = CH;
         const float r2_sc = p.r2_sc;
         const int lane = threadIdx.x & 31;
         for (;;) {
@@ -627,92 +637,187 @@ template <int NE, int MINB, int STAGES, bool EXACT> __global__ void __launch_bou
             const int b = where.x, vs = where.y;
             const int v0 = vs + slot * 2;
             const bool active = v0 < nv;
-            unsigned char *stage = stage_mem + s * TmaCfg<NE, STAGES>::stage_bytes;
+            unsigned char *stage = stage_mem + s * Cfg::stage_bytes;
             float4 *sraw = reinterpret_cast<float4 *>(stage) + slot;
             const SampleTab<NE> &T = *reinterpret_cast<const SampleTab<NE> *>(stage + (NE + 1) * kPlaneBytes);   // kdec = -te log2(e), unscaled
             constexpr int kPlaneF4 = kPlaneBytes / 16;
             const pk zero = splat<pk>(0.f);
-            AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
-            if (active) {
+            if constexpr (MODE != 0) {
+                // Register-resident variant: every echo is read from the stage ONCE.  Echo 0 pre-filters background chunks;
+                // the ragged test rides along with pass 1 on the ALU pipe; y stays in registers for pass 2.
+                float4 raw0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) raw0 = sraw[0];
+                const bool nz0 = raw0.x != 0.f || raw0.y != 0.f || raw0.z != 0.f || raw0.w != 0.f;
+                bool slow = false;
+                if (!__any_sync(0xffffffffu, nz0)) {
+                    // echo 0 is zero across the chunk: background unless a later echo is not (then the chunk is ragged)
+                    AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
+                    if (active) {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    if (EXACT || e < ne) {
-                        RawEcho<pk> raw;
-                        raw.v = sraw[e * kPlaneF4];
-                        abs_range(ar, raw);
+                        for (int e = 1; e < NE; ++e) {
+                            if (EXACT || e < ne) {
+                                RawEcho<pk> raw;
+                                raw.v = sraw[e * kPlaneF4];
+                                abs_range(ar, raw);
+                            }
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
+                        if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[s]);
+                        continue;
+                    }
+                    slow = true;
+                }
+                pk phi_t = zero, r2s = zero;                       // r2s = R2* in 1/s
+                if (active) {
+                    const float4 m4 = sraw[ne * kPlaneF4];
+                    phi_t = mk(m4.x, m4.z);
+                    r2s = vmul(r2_sc, mk(m4.y, m4.w));
+                }
+                cx<pk> y[NE];
+                [[maybe_unused]] pk d2[MODE == 1 ? NE : 1];
+                cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
+                if (!slow) {
+                    AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (EXACT || e < ne) {
+                            const EchoRec R = T.r[e];
+                            const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
+                            if constexpr (MODE == 1) d2[e] = vmul(m.d, m.d);
+                            RawEcho<pk> raw;
+                            raw.v = e == 0 ? raw0 : sraw[e * kPlaneF4];
+                            abs_range(ar, raw);
+                            y[e] = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
+                            cmac(rw, R.pw_re, R.pw_im, y[e]);
+                            cmac(rf, R.pf_re, R.pf_im, y[e]);
+                            cmac(tw, R.tpw_re, R.tpw_im, y[e]);
+                            cmac(tf, R.tpf_re, R.tpf_im, y[e]);
+                        }
+                    }
+                    slow = __any_sync(0xffffffffu, active && is_ragged(ar));
+                }
+                if (!slow) {
+                    pk lsum = zero;
+                    cx<pk> K = czero<pk>();
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (EXACT || e < ne) {
+                            const EchoRec R = T.r[e];
+                            pk dd;
+                            if constexpr (MODE == 1) dd = d2[e]; else dd = fast_ex2(vmul(2.0f * R.kdec, r2s));
+                            const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                            const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
+                            const cx<pk> r{vsub(yhat.re, y[e].re), vsub(yhat.im, y[e].im)};
+                            const cx<pk> w{vmul(dd, r.re), vmul(dd, r.im)};
+                            lsum = vfma(w.re, r.re, lsum);
+                            lsum = vfma(w.im, r.im, lsum);
+                            const cx<pk> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
+                            K.re = vfma(w.re, g.re, K.re);
+                            K.re = vfma(w.im, g.im, K.re);
+                            K.im = vfma(w.re, g.im, K.im);
+                            K.im = vfma(vneg(w.im), g.re, K.im);
+                        }
+                    }
+                    if (active) {
+                        loss_part += hsum(lsum);
+                        st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<pk>{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * r2_sc * p.inv_n, K.re)});
+                    }
+                } else if (active) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                        float ls, gphi, gr2;
+                        a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
+                                                r2_sc, ls, gphi, gr2);
+                        loss_part += ls;
+                        reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
                     }
                 }
-            }
-            // background: every component of every voxel of the warp is exactly zero -> loss 0, gradient 0
-            if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
-                if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
-                continue;
-            }
-            const bool warp_ragged = __any_sync(0xffffffffu, active && is_ragged(ar));
-            pk phi_t = zero, r2s = zero;                       // r2s = R2* in 1/s
-            if (active) {
-                const float4 m4 = sraw[ne * kPlaneF4];
-                phi_t = mk(m4.x, m4.z);
-                r2s = vmul(r2_sc, mk(m4.y, m4.w));
-            }
-            pk d2[NE];
-            cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
-            const bool fast = active && !warp_ragged;
-            if (fast) {
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    if (EXACT || e < ne) {
-                        const EchoRec R = T.r[e];
-                        const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
-                        d2[e] = vmul(m.d, m.d);
-                        RawEcho<pk> raw;
-                        raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
-                        const cx<pk> y = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
-                        // park y in this thread's own 16 bytes of the stage (the raw echo is no longer needed): 24 fewer
-                        // live registers across pass 2 than keeping it, for 6 STS + 6 LDS
-                        sraw[e * kPlaneF4] = make_float4(y.re.d.x, y.re.d.y, y.im.d.x, y.im.d.y);
-                        cmac(rw, R.pw_re, R.pw_im, y);
-                        cmac(rf, R.pf_re, R.pf_im, y);
-                        cmac(tw, R.tpw_re, R.tpw_im, y);
-                        cmac(tf, R.tpf_re, R.tpf_im, y);
+            } else {
+                AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
+                if (active) {
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (EXACT || e < ne) {
+                            RawEcho<pk> raw;
+                            raw.v = sraw[e * kPlaneF4];
+                            abs_range(ar, raw);
+                        }
                     }
                 }
-            }
-            if (fast) {
-                pk lsum = zero;
-                cx<pk> K = czero<pk>();
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    if (EXACT || e < ne) {
-                        const EchoRec R = T.r[e];
-                        const float4 yv = sraw[e * kPlaneF4];
-                        const cx<pk> y{mk(yv.x, yv.y), mk(yv.z, yv.w)};
-                        const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
-                        const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
-                        const cx<pk> r{vsub(yhat.re, y.re), vsub(yhat.im, y.im)};
-                        const cx<pk> w{vmul(d2[e], r.re), vmul(d2[e], r.im)};
-                        lsum = vfma(w.re, r.re, lsum);
-                        lsum = vfma(w.im, r.im, lsum);
-                        const cx<pk> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
-                        K.re = vfma(w.re, g.re, K.re);
-                        K.re = vfma(w.im, g.im, K.re);
-                        K.im = vfma(w.re, g.im, K.im);
-                        K.im = vfma(vneg(w.im), g.re, K.im);
+                // background: every component of every voxel of the warp is exactly zero -> loss 0, gradient 0
+                if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
+                    if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    continue;
+                }
+                const bool warp_ragged = __any_sync(0xffffffffu, active && is_ragged(ar));
+                pk phi_t = zero, r2s = zero;                       // r2s = R2* in 1/s
+                if (active) {
+                    const float4 m4 = sraw[ne * kPlaneF4];
+                    phi_t = mk(m4.x, m4.z);
+                    r2s = vmul(r2_sc, mk(m4.y, m4.w));
+                }
+                pk d2[NE];
+                cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
+                const bool fast = active && !warp_ragged;
+                if (fast) {
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (EXACT || e < ne) {
+                            const EchoRec R = T.r[e];
+                            const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
+                            d2[e] = vmul(m.d, m.d);
+                            RawEcho<pk> raw;
+                            raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
+                            const cx<pk> y = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
+                            // park y in this thread's own 16 bytes of the stage (the raw echo is no longer needed): 24 fewer
+                            // live registers across pass 2 than keeping it, for 6 STS + 6 LDS
+                            sraw[e * kPlaneF4] = make_float4(y.re.d.x, y.re.d.y, y.im.d.x, y.im.d.y);
+                            cmac(rw, R.pw_re, R.pw_im, y);
+                            cmac(rf, R.pf_re, R.pf_im, y);
+                            cmac(tw, R.tpw_re, R.tpw_im, y);
+                            cmac(tf, R.tpf_re, R.tpf_im, y);
+                        }
                     }
                 }
-                loss_part += hsum(lsum);
-                st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<pk>{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * r2_sc * p.inv_n, K.re)});
-            } else if (active) {
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    float ls, gphi, gr2;
-                    // the table in the stage carries the unscaled decay constant: hand the slow path R2* in 1/s
-                    a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
-                                            r2_sc, ls, gphi, gr2);
-                    loss_part += ls;
-                    reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+                if (fast) {
+                    pk lsum = zero;
+                    cx<pk> K = czero<pk>();
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        if (EXACT || e < ne) {
+                            const EchoRec R = T.r[e];
+                            const float4 yv = sraw[e * kPlaneF4];
+                            const cx<pk> y{mk(yv.x, yv.y), mk(yv.z, yv.w)};
+                            const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                            const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
+                            const cx<pk> r{vsub(yhat.re, y.re), vsub(yhat.im, y.im)};
+                            const cx<pk> w{vmul(d2[e], r.re), vmul(d2[e], r.im)};
+                            lsum = vfma(w.re, r.re, lsum);
+                            lsum = vfma(w.im, r.im, lsum);
+                            const cx<pk> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
+                            K.re = vfma(w.re, g.re, K.re);
+                            K.re = vfma(w.im, g.im, K.re);
+                            K.im = vfma(w.re, g.im, K.im);
+                            K.im = vfma(vneg(w.im), g.re, K.im);
+                        }
+                    }
+                    loss_part += hsum(lsum);
+                    st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<pk>{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * r2_sc * p.inv_n, K.re)});
+                } else if (active) {
+    #pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                        float ls, gphi, gr2;
+                        // the table in the stage carries the unscaled decay constant: hand the slow path R2* in 1/s
+                        a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
+                                                r2_sc, ls, gphi, gr2);
+                        loss_part += ls;
+                        reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+                    }
                 }
             }
             __syncwarp();
@@ -774,13 +879,14 @@ static int coprime_stride(int n) {
     return s % n;
 }
 
-template <typename K> static int launch_tma(const SolveParams &p, cudaStream_t st, K kernel, int smem) {
+template <typename K> static int launch_tma(SolveParams p, cudaStream_t st, K kernel, int smem, int tile_vox) {
+    p.tile_stride = coprime_stride((p.nv + tile_vox - 1) / tile_vox);
     int dev = 0, sms = 0, occ = 0;
     IG_CUDA(cudaGetDevice(&dev));
     IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     IG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads + 32, smem));
-    const long tiles = static_cast<long>(p.nb) * ((p.nv + kTileVox - 1) / kTileVox);
+    const long tiles = static_cast<long>(p.nb) * ((p.nv + tile_vox - 1) / tile_vox);
     long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
     if (g > tiles) g = tiles;
     kernel<<<static_cast<int>(g), kThreads + 32, smem, st>>>(p);
@@ -889,14 +995,25 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
         if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
         static const int no_tma = [] { const char *e = getenv("IG_A2A_NO_TMA"); return e ? atoi(e) : 0; }();         // A/B knob
         if (packed && !no_tma) {
-            // two blocks per SM with as many ring stages as fit the 227 KB of shared memory (measured: 2 x 3 stages at 96
-            // registers = 3 x 2 stages at 72 registers within noise for ne = 6; the former does not spill)
+            // two blocks per SM with as many ring stages as fit the 227 KB of shared memory
             constexpr int kBudget = 216 * 1024;
-            p.tile_stride = coprime_stride((nv + kTileVox - 1) / kTileVox);
-            if (ne == NE && NE <= 8 && 2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3, true>, TmaCfg<NE, 3>::smem_bytes);
-            if (2 * TmaCfg<NE, 3>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 3, false>, TmaCfg<NE, 3>::smem_bytes);
-            if (2 * TmaCfg<NE, 2>::smem_bytes <= kBudget) return launch_tma(p, st, a2a_loss_tma_kernel<NE, 2, 2, false>, TmaCfg<NE, 2>::smem_bytes);
-            return launch_tma(p, st, a2a_loss_tma_kernel<NE, 1, 3, false>, TmaCfg<NE, 3>::smem_bytes);
+            static const int variant = [] { const char *e = getenv("IG_A2A_VARIANT"); return e ? atoi(e) : 0; }();     // experiment knob
+            auto go = [&](auto st_c, auto ch_c, auto minb_c, auto mode_c) {
+                constexpr int S = decltype(st_c)::value, C = decltype(ch_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
+                using Cfg = TmaCfg<NE, S, C>;
+                if (ne == NE && NE <= 8) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, true, C, MD>, Cfg::smem_bytes, Cfg::tile_vox);
+                return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD>, Cfg::smem_bytes, Cfg::tile_vox);
+            };
+            using M0 = std::integral_constant<int, 0>;
+            using std::integral_constant;
+            if constexpr (NE <= 8) {
+                // y (and d^2) stay in registers between the two passes: 95 registers at NE = 6, no spills
+                if (variant == 0) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
+                if (variant == 2) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+            }
+            if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, M0{});
+            if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(integral_constant<int, 2>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, M0{});
+            return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 1>{}, M0{});
         }
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
