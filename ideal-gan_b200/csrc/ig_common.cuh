@@ -239,9 +239,10 @@ template <int NE, typename V> __device__ __forceinline__ Mod<V> modulator(const 
     m.dinv = fast_ex2(vneg(lg));
     return m;
 }
-template <typename V> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
+template <typename V, bool BIP = true> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
     Mod<V> m;
-    unit_phasor(vfma(R.sgn, bturn, vmul(R.kphi, phi_t)), m.c, m.s);
+    if constexpr (BIP) unit_phasor(vfma(R.sgn, bturn, vmul(R.kphi, phi_t)), m.c, m.s);
+    else unit_phasor(vmul(R.kphi, phi_t), m.c, m.s);
     const V lg = vmul(R.kdec, r2);
     m.d = fast_ex2(lg);
     m.dinv = fast_ex2(vneg(lg));
@@ -342,6 +343,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// tiled TMA load of a 3-D box described by a tensor map (kernel parameter, __grid_constant__); coordinates innermost first
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
 // barrier among the first `count` threads of the block (id 1; id 0 is __syncthreads)

@@ -7,6 +7,7 @@
 //     rho = M^+ y          yhat = M rho          S_hat_e = Wp_e yhat_e         (Wp_e = 1 / Wm_e)
 // The pseudo-inverse M^+ depends only on the sample's echo times, so it is a shared-memory table and the
 // "solve" is a 2 x ne complex contraction held in registers.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "ig_common.cuh"
@@ -537,12 +538,14 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
 // =================================================================================================
 // TMA-pipelined variant of the fused objective (packed path, no materialised outputs): the headline kernel.
 //
-// Warp-specialised persistent blocks: 8 consumer warps + 1 producer warp.  The producer's lane 0 streams
-// each tile (ne echo planes + the PM row, 512 voxels = 4 KB per plane) into a ring of shared-memory
-// stages with cp.async.bulk (TMA) completing on a "full" mbarrier; consumers read their 16 bytes per
-// plane with conflict-free LDS.128, and release the stage through an "empty" mbarrier as soon as pass 1
-// has turned the raw echoes into registers.  Loads therefore cost the consumers no registers, no address
-// arithmetic and no long-scoreboard stalls, and up to STAGES tiles per block are in flight to HBM.
+// Warp-specialised persistent blocks: NCW consumer warps + 1 producer warp.  The producer's lane 0 claims tiles
+// from a global counter and streams each one (ne echo planes + the PM row + the sample's echo records) into a
+// ring of shared-memory stages with TMA -- one 3-D tensor-map box for all echo planes, one for the PM row --
+// completing on a "full" mbarrier.  Consumer warps draw 64-voxel chunks of the ring from a shared counter,
+// read their 16 bytes per plane with conflict-free LDS.128 exactly once, keep y and d^2 in registers between
+// the two passes (MODE 1; MODE 0 parks y in the stage for NE > 8) and release the stage through an "empty"
+// mbarrier.  Loads therefore cost the consumers no address arithmetic and no long-scoreboard stalls, and up
+// to STAGES tiles per block are in flight to HBM.
 // =================================================================================================
 constexpr int kChunkVox = 64;                          // voxels per consumer-warp chunk (two per lane)
 template <int NE, int STAGES, int CH> struct TmaCfg {
@@ -555,7 +558,9 @@ template <int NE, int STAGES, int CH> struct TmaCfg {
 
 // Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
 // cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
-template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE> __global__ void __launch_bounds__(kThreads + 32, MINB) a2a_loss_tma_kernel(const SolveParams p) {
+template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE, int NCW, bool TMAP>
+__global__ void __launch_bounds__(NCW * 32 + 32, MINB)
+a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map_acq, const __grid_constant__ CUtensorMap map_pm) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ int2 stage_tile[STAGES];             // (sample, first voxel) of the tile in each stage; sample < 0 = end
@@ -575,45 +580,62 @@ template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE> __global__
     }
     __syncthreads();
     float loss_part = 0.f;
-    if (threadIdx.x >= kThreads) {
+    constexpr int kConsumers = NCW * 32;
+    if (threadIdx.x >= kConsumers) {
         // ---------------- producer warp ----------------
-        if (threadIdx.x == kThreads) {
-            unsigned *next_tile = reinterpret_cast<unsigned *>(p.scratch) + 1;
-            const size_t plane_stride = static_cast<size_t>(nv) * 2;
+        // Lane 0 owns the work counter, the barriers and the copies.  With tensor maps (TMAP) a tile is three TMA
+        // instructions: one 3-D box {256 floats, tile rows, ne planes} for all echoes, one for the PM row, one bulk copy for the
+        // echo records.  Without (nv not a multiple of 128) it is ne + 2 bulk copies, ~130 cycles of issue each.
+        const int lane = threadIdx.x & 31;
+        unsigned *next_tile = reinterpret_cast<unsigned *>(p.scratch) + 1;
+        const size_t plane_stride = static_cast<size_t>(nv) * 2;
+        // the claim for the next tile (an L2 atomic) is in flight while this one is waited for and issued
+        // The counter is bumped with a FLOAT atomic add (exact up to 2^24 work items; zero bits = 0.0f, so the scratch header
+        // is reused as is): ptxas warp-aggregates every integer atom.add/inc, and the shuffle it puts right behind the
+        // atomic would make the producer sit out the full L2 round trip (~1400 cycles) for each tile.
+        auto claim_async = [&]() -> float {
+            float k;
+            asm volatile("atom.global.add.f32 %0, [%1], 0f3F800000;" : "=f"(k) : "l"(next_tile) : "memory");
+            return k;
+        };
+        float k_nxt = 0.f;
+        if (lane == 0) k_nxt = claim_async();
+        int ends_left = (NCW + CH - 1) / CH;
+        for (int it = 0;; ++it) {
+            const int s = it % STAGES;
+            const int k = static_cast<int>(__shfl_sync(0xffffffffu, k_nxt, 0));
+            const bool end = k >= total;
+            if (lane == 0 && !end) k_nxt = claim_async();
             // Tiles of a sample are visited in a strided order so that cheap background tiles (load-bound) and tissue
             // tiles (math-bound) are in flight together chip-wide instead of in alternating phases.
-            auto claim = [&]() -> int2 {
-                const int k = static_cast<int>(atomicAdd(next_tile, 1u));
-                if (k >= total) return make_int2(-1, 0);
-                const int b = k / tiles_ps;
-                const int j = k - b * tiles_ps;
-                const int vs = static_cast<int>((static_cast<unsigned long long>(j) * static_cast<unsigned>(p.tile_stride)) % static_cast<unsigned>(tiles_ps)) * kTileVox;
-                return make_int2(b, vs);
-            };
-            // the claim for the next tile is in flight (an L2 atomic, ~1 us under load) while this one is waited for and issued
-            int2 nxt = claim();
-            int ends_left = (kThreads / 32 + CH - 1) / CH;
-            for (int it = 0;; ++it) {
-                const int s = it % STAGES;
-                const int2 cur = nxt;
-                if (cur.x >= 0) nxt = claim();
+            const int b = end ? -1 : k / tiles_ps;
+            const int j = k - b * tiles_ps;
+            const int vs = end ? 0 : static_cast<int>((static_cast<unsigned>(j) * static_cast<unsigned>(p.tile_stride)) % static_cast<unsigned>(tiles_ps)) * kTileVox;   // < 2^32: see coprime_stride
+            const int nvox = (nv - vs < kTileVox) ? nv - vs : kTileVox;
+            const uint32_t bytes = TMAP ? static_cast<uint32_t>(kPlaneBytes) : static_cast<uint32_t>(nvox) * 8u;   // a TMA box counts in full (out-of-range rows arrive as zeros)
+            unsigned char *stage = stage_mem + s * Cfg::stage_bytes;
+            if (lane == 0) {
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-                stage_tile[s] = cur;
-                if (cur.x < 0) {
-                    // end marker: completes the phase without data.  Every consumer warp draws exactly one chunk past
-                    // the data, so enough marker stages are published to cover all of them.
-                    mbar_arrive(&full_bar[s]);
-                    if (--ends_left == 0) break;
-                    continue;
+                stage_tile[s] = make_int2(b, vs);
+                // end marker: completes the phase without data
+                if (end) mbar_arrive(&full_bar[s]);
+                else mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + Cfg::tab_bytes);
+            }
+            __syncwarp();
+            if (end) {
+                // every consumer warp draws exactly one chunk past the data: publish enough marker stages to cover all of them
+                if (--ends_left == 0) break;
+                continue;
+            }
+            if (lane == 0) {
+                if constexpr (TMAP) {
+                    tma_load_3d(stage, &map_acq, 0, vs >> 7, b * ne, &full_bar[s]);
+                    tma_load_3d(stage + ne * kPlaneBytes, &map_pm, 0, vs >> 7, b, &full_bar[s]);
+                } else {
+                    const float *src = p.acqs + (static_cast<size_t>(b) * ne * nv + vs) * 2;
+                    for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + e * plane_stride, bytes, &full_bar[s]);
+                    bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
                 }
-                const int b = cur.x, vs = cur.y;
-                const int nvox = (nv - vs < kTileVox) ? nv - vs : kTileVox;
-                const uint32_t bytes = static_cast<uint32_t>(nvox) * 8u;
-                unsigned char *stage = stage_mem + s * Cfg::stage_bytes;
-                mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + Cfg::tab_bytes);
-                const float *src = p.acqs + (static_cast<size_t>(b) * ne * nv + vs) * 2;
-                for (int e = 0; e < ne; ++e) bulk_g2s(stage + e * kPlaneBytes, src + e * plane_stride, bytes, &full_bar[s]);
-                bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
                 bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, Cfg::tab_bytes, &full_bar[s]);
             }
         }
@@ -685,7 +707,7 @@ template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE> __global__
                     for (int e = 0; e < NE; ++e) {
                         if (EXACT || e < ne) {
                             const EchoRec R = T.r[e];
-                            const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
+                            const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
                             if constexpr (MODE == 1) d2[e] = vmul(m.d, m.d);
                             RawEcho<pk> raw;
                             raw.v = e == 0 ? raw0 : sraw[e * kPlaneF4];
@@ -769,7 +791,7 @@ template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE> __global__
                     for (int e = 0; e < NE; ++e) {
                         if (EXACT || e < ne) {
                             const EchoRec R = T.r[e];
-                            const Mod<pk> m = modulator_rec(R, phi_t, r2s, zero);
+                            const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
                             d2[e] = vmul(m.d, m.d);
                             RawEcho<pk> raw;
                             raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
@@ -872,24 +894,48 @@ template <typename K1, typename K2> static int launch_persistent(bool packed, co
 
 // a stride near 0.618 * n that is coprime with n: consecutive work items land on distant tiles of the slice
 static int coprime_stride(int n) {
-    if (n <= 2) return 1;
+    if (n <= 2 || n > 46340) return 1;      // j * stride must fit 32 bits
     int s = static_cast<int>(n * 0.6180339887) | 1;
     auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
     while (gcd(s, n) != 1) s += 2;
     return s % n;
 }
 
-template <typename K> static int launch_tma(SolveParams p, cudaStream_t st, K kernel, int smem, int tile_vox) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// `planes` complex planes of nv voxels, `plane_stride` floats apart, seen as {256 floats, nv / 128 rows, planes}; box = {256, tile_rows, box_planes}
+static bool plane_tensor_map(CUtensorMap *m, const float *base, int nv, long planes, long plane_stride, int tile_rows, int box_planes) {
+    const EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {256, static_cast<cuuint64_t>(nv / 128), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t strides[2] = {1024, static_cast<cuuint64_t>(plane_stride) * 4};
+    const cuuint32_t box[3] = {256, static_cast<cuuint32_t>(tile_rows), static_cast<cuuint32_t>(box_planes)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename K> static int launch_tma(SolveParams p, cudaStream_t st, K kernel, int smem, int tile_vox, int threads, const CUtensorMap &ma, const CUtensorMap &mp) {
     p.tile_stride = coprime_stride((p.nv + tile_vox - 1) / tile_vox);
     int dev = 0, sms = 0, occ = 0;
     IG_CUDA(cudaGetDevice(&dev));
     IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     IG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads + 32, smem));
+    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     const long tiles = static_cast<long>(p.nb) * ((p.nv + tile_vox - 1) / tile_vox);
     long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
     if (g > tiles) g = tiles;
-    kernel<<<static_cast<int>(g), kThreads + 32, smem, st>>>(p);
+    kernel<<<static_cast<int>(g), threads, smem, st>>>(p, ma, mp);
     IG_CUDA(cudaGetLastError());
     return 0;
 }
@@ -993,27 +1039,36 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
-        static const int no_tma = [] { const char *e = getenv("IG_A2A_NO_TMA"); return e ? atoi(e) : 0; }();         // A/B knob
-        if (packed && !no_tma) {
-            // two blocks per SM with as many ring stages as fit the 227 KB of shared memory
+        if (packed) {
+            // Two blocks per SM, 8 consumer warps + 1 producer warp each, 512-voxel tiles, as many ring stages as fit the
+            // 227 KB of shared memory.  Measured alternatives (profiles/history_r01.md): smaller tiles, one 17-warp block per
+            // SM, 10-12 consumer warps per block and batched tile claims are all slower.
             constexpr int kBudget = 216 * 1024;
-            static const int variant = [] { const char *e = getenv("IG_A2A_VARIANT"); return e ? atoi(e) : 0; }();     // experiment knob
-            auto go = [&](auto st_c, auto ch_c, auto minb_c, auto mode_c) {
-                constexpr int S = decltype(st_c)::value, C = decltype(ch_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
+            auto go = [&](auto st_c, auto minb_c, auto mode_c) {
+                constexpr int S = decltype(st_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
+                constexpr int C = 8, W = 8;
                 using Cfg = TmaCfg<NE, S, C>;
-                if (ne == NE && NE <= 8) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, true, C, MD>, Cfg::smem_bytes, Cfg::tile_vox);
-                return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD>, Cfg::smem_bytes, Cfg::tile_vox);
+                constexpr bool exact_ok = NE <= 8;
+                CUtensorMap ma{}, mp{};
+                // tensor maps need whole 128-voxel rows; otherwise the tile is fetched plane by plane with bulk copies
+                const bool tmap = nv % 128 == 0 && plane_tensor_map(&ma, acqs_d, nv, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, C / 2, ne) &&
+                                  plane_tensor_map(&mp, pm_d, nv, nb, pm_bstride, C / 2, 1);
+                const bool exact = exact_ok && ne == NE;
+                if (tmap) {
+                    if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+                    return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+                }
+                if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+                return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
             };
-            using M0 = std::integral_constant<int, 0>;
-            using std::integral_constant;
-            if constexpr (NE <= 8) {
-                // y (and d^2) stay in registers between the two passes: 95 registers at NE = 6, no spills
-                if (variant == 0) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
-                if (variant == 2) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
-            }
-            if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, M0{});
-            if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(integral_constant<int, 2>{}, integral_constant<int, 8>{}, integral_constant<int, 2>{}, M0{});
-            return go(integral_constant<int, 3>{}, integral_constant<int, 8>{}, integral_constant<int, 1>{}, M0{});
+            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+            using I3 = std::integral_constant<int, 3>;
+            // up to 8 echoes y (and d^2) stay in registers between the two passes (95 registers at NE = 6, no spills);
+            // beyond that y is parked in the thread's own 16 bytes of the stage
+            if constexpr (NE <= 8) return go(I3{}, I2{}, I1{});
+            if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{});
+            if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{});
+            return go(I3{}, I1{}, I0{});
         }
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });

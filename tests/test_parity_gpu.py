@@ -200,7 +200,9 @@ def test_acq_to_acq_and_config2_loss_vs_reference_vectors(golden, name):
     assert_close(host(gl_b), host(gl), 1e-6)
 
 
-@pytest.mark.parametrize("hw", [(9, 7), (48, 64)])
+# (9, 7): odd voxel count -> scalar kernels; (48, 64): whole 512-voxel tiles through tensor-map TMA; (40, 48): 128-voxel
+# rows but a ragged last tile (out-of-range rows of the TMA box); (30, 34): even but not a multiple of 128 -> bulk-copy ring
+@pytest.mark.parametrize("hw", [(9, 7), (48, 64), (40, 48), (30, 34)])
 @pytest.mark.parametrize("ne", [2, 5, 6, 12])
 def test_acq_to_acq_family_vs_oracle(hw, ne):
     rng = np.random.default_rng(31 + ne)
