@@ -351,6 +351,9 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0,
                  "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
+// programmatic dependent launch (PDL): wait for the kernel this launch depends on / let the dependent kernel start early
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // barrier among the first `count` threads of the block (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void named_barrier(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 

@@ -153,71 +153,107 @@ __device__ __forceinline__ void write_grads(float *g_b, int rows_or_ch, int nv, 
     }
 }
 
+// one thread's voxels of sample b starting at v0: decode, all echoes, write-out; returns the thread's loss partial
+template <int NE, typename V, int MODEL, int MODE>
+__device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTab<NE> &T, int b, int v0) {
+    const int nv = p.nv, ne = p.ne;
+    const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * p.rows_or_ch
+                                                        : static_cast<size_t>(p.rows_or_ch) * nv * 2;
+    const Voxel<V> x = decode<V, MODEL>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags);
+    const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    Adj<V> a;
+    a.sg = czero<V>(); a.sgc = czero<V>(); a.tq = czero<V>(); a.q = czero<V>(); a.bq = splat<V>(0.f);
+    V lsum = splat<V>(0.f);
+    // issue every upstream / measurement load before the math so each thread has ne loads in flight
+    cx<V> in[NE];
+    if constexpr (MODE != MODE_FWD) {
+        const float *src = (MODE == MODE_BWD ? p.gout : p.acqs) + acq_b;
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            if (e < ne) in[e] = ld_cx(src + static_cast<size_t>(e) * nv * 2, v0, V{});
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            V c, s;
+            unit_phasor(vfma(T.r[e].sgn, x.bturn, vmul(T.r[e].kphi, x.phi_t)), c, s);
+            const V d = fast_ex2(vmul(T.r[e].kdec, x.r2));
+            const cx<V> w{vmul(d, c), vmul(d, s)};
+            const cx<V> yhat = caffine(x.rhoW, T.r[e].c_re, T.r[e].c_im, x.rhoF);
+            const cx<V> shat = cmulv(w, yhat);
+            if constexpr (MODE == MODE_FWD) {
+                st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+            } else {
+                cx<V> G;
+                if constexpr (MODE == MODE_BWD) {
+                    G = in[e];
+                } else {
+                    G = cx<V>{mask_sub(shat.re, in[e].re), mask_sub(shat.im, in[e].im)};
+                    lsum = vfma(G.re, G.re, lsum);
+                    lsum = vfma(G.im, G.im, lsum);
+                    if (p.out) st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                }
+                const cx<V> g = cmulc(w, G);
+                a.sg.re = vadd(a.sg.re, g.re);
+                a.sg.im = vadd(a.sg.im, g.im);
+                cmac(a.sgc, T.r[e].c_re, -T.r[e].c_im, g);
+                const cx<V> q = cmulc(g, yhat);
+                a.tq.re = vfma(T.r[e].te, q.re, a.tq.re);
+                a.tq.im = vfma(T.r[e].te, q.im, a.tq.im);
+                if constexpr (MODEL == IG_MODEL_FFPD) { a.q.re = vadd(a.q.re, q.re); a.q.im = vadd(a.q.im, q.im); }
+                if constexpr (MODEL != IG_MODEL_FFPD) a.bq = vfma(T.r[e].sgn, q.im, a.bq);
+            }
+        }
+    }
+    if constexpr (MODE != MODE_FWD) {
+        const float scale = (MODE == MODE_LOSS) ? 2.0f * p.inv_n : 1.0f;
+        write_grads<V, MODEL>(p.gmaps + b * map_elems, p.rows_or_ch, nv, v0, p.flags, x, a, p.r2_sc, scale);
+    }
+    return hsum(lsum);
+}
+
 template <int NE, typename V, int MODEL, int MODE>
 __global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
     __shared__ SampleTab<NE> T;
     const int b = blockIdx.y;
     stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
     const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
-    const bool active = v0 < p.nv;
+    if (v0 < p.nv) ideal_voxels<NE, V, MODEL, MODE>(p, T, b, v0);
+}
+
+// Fused objective: a persistent grid (one resident wave), each block walking a contiguous range of (sample, tile)
+// work items and taking part in the loss reduction ONCE at the end -- with one block per tile the 18 k ticket atomics
+// of a 64-slice batch all hit one address and every block sits out its own L2 round trip before it can retire.
+template <int NE, typename V, int MODEL>
+__global__ void __launch_bounds__(kThreads) ideal_loss_kernel(const FwdParams p) {
+    __shared__ SampleTab<NE> T;
+    const int tiles_ps = (p.nv + kThreads * lanes<V>::n - 1) / (kThreads * lanes<V>::n);
+    const long total = static_cast<long>(p.nb) * tiles_ps;
+    const int tile_end = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
+    int cur_b = -1;
     float loss_part = 0.f;
-    if (active) {
-        const int nv = p.nv, ne = p.ne;
-        const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * p.rows_or_ch
-                                                            : static_cast<size_t>(p.rows_or_ch) * nv * 2;
-        const Voxel<V> x = decode<V, MODEL>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags);
-        const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
-        Adj<V> a;
-        a.sg = czero<V>(); a.sgc = czero<V>(); a.tq = czero<V>(); a.q = czero<V>(); a.bq = splat<V>(0.f);
-        V lsum = splat<V>(0.f);
-        // issue every upstream / measurement load before the math so each thread has ne loads in flight
-        cx<V> in[NE];
-        if constexpr (MODE != MODE_FWD) {
-            const float *src = (MODE == MODE_BWD ? p.gout : p.acqs) + acq_b;
-#pragma unroll
-            for (int e = 0; e < NE; ++e)
-                if (e < ne) in[e] = ld_cx(src + static_cast<size_t>(e) * nv * 2, v0, V{});
+    for (int tile = static_cast<int>(total * blockIdx.x / gridDim.x); tile < tile_end; ++tile) {
+        const int b = tile / tiles_ps;
+        if (b != cur_b) {
+            if (cur_b >= 0) __syncthreads();          // everyone is done reading the previous sample's table
+            stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+            cur_b = b;
         }
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            if (e < ne) {
-                V c, s;
-                unit_phasor(vfma(T.r[e].sgn, x.bturn, vmul(T.r[e].kphi, x.phi_t)), c, s);
-                const V d = fast_ex2(vmul(T.r[e].kdec, x.r2));
-                const cx<V> w{vmul(d, c), vmul(d, s)};
-                const cx<V> yhat = caffine(x.rhoW, T.r[e].c_re, T.r[e].c_im, x.rhoF);
-                const cx<V> shat = cmulv(w, yhat);
-                if constexpr (MODE == MODE_FWD) {
-                    st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
-                } else {
-                    cx<V> G;
-                    if constexpr (MODE == MODE_BWD) {
-                        G = in[e];
-                    } else {
-                        G = cx<V>{mask_sub(shat.re, in[e].re), mask_sub(shat.im, in[e].im)};
-                        lsum = vfma(G.re, G.re, lsum);
-                        lsum = vfma(G.im, G.im, lsum);
-                        if (p.out) st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
-                    }
-                    const cx<V> g = cmulc(w, G);
-                    a.sg.re = vadd(a.sg.re, g.re);
-                    a.sg.im = vadd(a.sg.im, g.im);
-                    cmac(a.sgc, T.r[e].c_re, -T.r[e].c_im, g);
-                    const cx<V> q = cmulc(g, yhat);
-                    a.tq.re = vfma(T.r[e].te, q.re, a.tq.re);
-                    a.tq.im = vfma(T.r[e].te, q.im, a.tq.im);
-                    if constexpr (MODEL == IG_MODEL_FFPD) { a.q.re = vadd(a.q.re, q.re); a.q.im = vadd(a.q.im, q.im); }
-                    if constexpr (MODEL != IG_MODEL_FFPD) a.bq = vfma(T.r[e].sgn, q.im, a.bq);
-                }
-            }
-        }
-        if constexpr (MODE != MODE_FWD) {
-            const float scale = (MODE == MODE_LOSS) ? 2.0f * p.inv_n : 1.0f;
-            write_grads<V, MODEL>(p.gmaps + b * map_elems, p.rows_or_ch, nv, v0, p.flags, x, a, p.r2_sc, scale);
-        }
-        loss_part = hsum(lsum);
+        const int v0 = ((tile - b * tiles_ps) * kThreads + threadIdx.x) * lanes<V>::n;
+        if (v0 < p.nv) loss_part += ideal_voxels<NE, V, MODEL, MODE_LOSS>(p, T, b, v0);
     }
-    if constexpr (MODE == MODE_LOSS) block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+}
+
+template <typename K> static int resident_grid(K kernel, int nb, int nv, int vpt, int *grid) {
+    int dev = 0, sms = 0, occ = 0;
+    IG_CUDA(cudaGetDevice(&dev));
+    IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0));
+    const long tiles = static_cast<long>(nb) * ((nv + kThreads * vpt - 1) / (kThreads * vpt));
+    const long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
+    *grid = static_cast<int>(g < tiles ? g : tiles);
+    return 0;
 }
 
 template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaStream_t st) {
@@ -229,7 +265,16 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
     }
     return dispatch_ne(p.ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        if (packed) {
+        if constexpr (MODE == MODE_LOSS) {
+            int grid = 1;
+            if (packed) {
+                if (int rc = resident_grid(ideal_loss_kernel<NE, pk, MODEL>, p.nb, p.nv, 2, &grid)) return rc;
+                ideal_loss_kernel<NE, pk, MODEL><<<grid, kThreads, 0, st>>>(p);
+            } else {
+                if (int rc = resident_grid(ideal_loss_kernel<NE, float, MODEL>, p.nb, p.nv, 1, &grid)) return rc;
+                ideal_loss_kernel<NE, float, MODEL><<<grid, kThreads, 0, st>>>(p);
+            }
+        } else if (packed) {
             ideal_kernel<NE, pk, MODEL, MODE><<<grid_for(p.nb, p.nv, 2), kThreads, 0, st>>>(p);
         } else {
             ideal_kernel<NE, float, MODEL, MODE><<<grid_for(p.nb, p.nv, 1), kThreads, 0, st>>>(p);

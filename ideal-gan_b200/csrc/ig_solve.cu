@@ -238,6 +238,11 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_fw
 // acq_to_acq backward.  Upstream G_e on S_hat (or g_e on |S_hat|: G = g S_hat / |S_hat|) and Gamma_s on rho/rho_sc.
 //   v_e = conj(Wp_e) G_e ; g_rho = Gamma / rho_sc + M^H v ; gy = (M^+)^H g_rho ; dL/dS_e = conj(Wm_e) gy_e
 //   X = sum_e te_e (conj(gy_e) y_e - conj(v_e) yhat_e) ; dL/dphi~ = 2 pi fm_sc Im X ; dL/dR~ = r2_sc Re X
+// Both sums collapse onto per-voxel accumulators, so nothing per echo stays live and the packed lanes fit:
+//   sum_e te_e conj(gy_e) y_e    = conj(g_w) t_w + conj(g_f) t_f        (t = M^+ (te . y), as in the fused objective)
+//   sum_e te_e conj(v_e) yhat_e  = conj(a_w) rho_w + conj(a_f) rho_f    (a_w = sum te_e v_e, a_f = sum te_e conj(c_e) v_e)
+// One loop over the echoes forms y_e and v_e from the same modulator; only dL/dS (optional) needs a second loop,
+// which recomputes the modulator instead of keeping six of them in registers.
 // =================================================================================================
 template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bwd_kernel(const SolveParams p) {
     __shared__ SampleTab<NE> T;
@@ -247,72 +252,96 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) a2a_bw
     if (v0 >= p.nv) return;
     const int nv = p.nv, ne = p.ne;
     const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    const size_t plane = static_cast<size_t>(nv) * 2;
     const V zero = splat<V>(0.f);
+    const bool only_mag = p.flags & IG_F_ONLY_MAG;
     V phi_t, r2;
     ld_pm<V, false>(p.pm + b * p.pm_bstride, v0, phi_t, r2);
-    Mod<V> m[NE];
-    cx<V> y[NE];
-    cx<V> rw = czero<V>(), rf = czero<V>();
+    cx<V> rw = czero<V>(), rf = czero<V>(), tw = czero<V>(), tf = czero<V>();
+    cx<V> gw = czero<V>(), gf = czero<V>(), aw = czero<V>(), af = czero<V>();
+    [[maybe_unused]] V dec[NE];          // decay per echo, kept for the magnitude upstream only
+    const bool direct = p.g_shat && !only_mag;
+    // every echo and upstream load is issued before the math: 2 ne 16-byte loads in flight per thread
+    cx<V> S[NE], G[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
-            m[e] = modulator(T, e, phi_t, r2, zero);
-            y[e] = demod(m[e], ld_cx(p.acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{}));
-            cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y[e]);
-            cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y[e]);
+            S[e] = ld_cx(p.acqs + acq_b + e * plane, v0, V{});
+            if (direct) G[e] = ld_cx(p.g_shat + acq_b + e * plane, v0, V{});
         }
     }
-    // pass over the upstream of S_hat: v_e, M^H v, and the -conj(v) yhat part of X
-    cx<V> gw = czero<V>(), gf = czero<V>(), X = czero<V>();
-    if (p.g_shat) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const EchoRec R = T.r[e];
+            const Mod<V> m = modulator_rec<V, false>(R, phi_t, r2, zero);
+            const cx<V> y = demod(m, S[e]);
+            cmac(rw, R.pw_re, R.pw_im, y);
+            cmac(rf, R.pf_re, R.pf_im, y);
+            cmac(tw, R.tpw_re, R.tpw_im, y);
+            cmac(tf, R.tpf_re, R.tpf_im, y);
+            dec[e] = m.d;
+            if (direct) {
+                const cx<V> v = demod_fwd(m, G[e]);
+                gw.re = vadd(gw.re, v.re);
+                gw.im = vadd(gw.im, v.im);
+                cmac(gf, R.c_re, -R.c_im, v);
+                aw.re = vfma(R.te, v.re, aw.re);
+                aw.im = vfma(R.te, v.im, aw.im);
+                cmac(af, R.te * R.c_re, -R.te * R.c_im, v);
+            }
+        }
+    }
+    if (p.g_shat && only_mag) {
+        // |S_hat| = d |yhat| ; G = g S_hat / |S_hat| ; v = conj(Wp) G = g d yhat / |yhat|  (0 where |yhat| = 0)
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
-                const cx<V> yhat = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
-                cx<V> G;
-                if (p.flags & IG_F_ONLY_MAG) {
-                    // |S_hat| = d |yhat| ; G = g S_hat / |S_hat| ; v = conj(Wp) G = g d yhat / |yhat|  (0 where |yhat| = 0)
-                    const V g = ld_real(p.g_shat + static_cast<size_t>(b) * ne * nv + static_cast<size_t>(e) * nv, v0, V{});
-                    V sc = zero;
+                const EchoRec R = T.r[e];
+                const cx<V> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                const V g = ld_real(p.g_shat + static_cast<size_t>(b) * ne * nv + static_cast<size_t>(e) * nv, v0, V{});
+                V sc = zero;
 #pragma unroll
-                    for (int l = 0; l < lanes<V>::n; ++l) {
-                        const float a2 = lane_get(yhat.re, l) * lane_get(yhat.re, l) + lane_get(yhat.im, l) * lane_get(yhat.im, l);
-                        lane_set(sc, l, a2 > 0.f ? lane_get(g, l) * lane_get(m[e].d, l) * rsqrtf(a2) : 0.f);
-                    }
-                    G = cscale(sc, yhat);            // this is v_e directly
-                } else {
-                    G = demod_fwd(m[e], ld_cx(p.g_shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, V{}));
+                for (int l = 0; l < lanes<V>::n; ++l) {
+                    const float a2 = lane_get(yhat.re, l) * lane_get(yhat.re, l) + lane_get(yhat.im, l) * lane_get(yhat.im, l);
+                    lane_set(sc, l, a2 > 0.f ? lane_get(g, l) * lane_get(dec[e], l) * rsqrtf(a2) : 0.f);
                 }
-                const cx<V> v = G;
+                const cx<V> v = cscale(sc, yhat);
                 gw.re = vadd(gw.re, v.re);
                 gw.im = vadd(gw.im, v.im);
-                cmac(gf, T.r[e].c_re, -T.r[e].c_im, v);
-                const cx<V> q = cmulc(v, yhat);
-                X.re = vfma(-T.r[e].te, q.re, X.re);
-                X.im = vfma(-T.r[e].te, q.im, X.im);
+                cmac(gf, R.c_re, -R.c_im, v);
+                aw.re = vfma(R.te, v.re, aw.re);
+                aw.im = vfma(R.te, v.im, aw.im);
+                cmac(af, R.te * R.c_re, -R.te * R.c_im, v);
             }
         }
     }
     if (p.g_rho) {
         const float inv = 1.0f / kRhoSc;
         const float *g_b = p.g_rho + static_cast<size_t>(b) * 2 * nv * 2;
-        const cx<V> a = ld_cx(g_b, v0, V{}), c = ld_cx(g_b + static_cast<size_t>(nv) * 2, v0, V{});
+        const cx<V> a = ld_cx(g_b, v0, V{}), c = ld_cx(g_b + plane, v0, V{});
         gw.re = vfma(inv, a.re, gw.re); gw.im = vfma(inv, a.im, gw.im);
         gf.re = vfma(inv, c.re, gf.re); gf.im = vfma(inv, c.im, gf.im);
     }
+    // X = conj(g_w) t_w + conj(g_f) t_f - conj(a_w) rho_w - conj(a_f) rho_f
+    cx<V> X = cmulc(gw, tw);
+    const cx<V> x1 = cmulc(gf, tf), x2 = cmulc(aw, rw), x3 = cmulc(af, rf);
+    X.re = vsub(vadd(X.re, x1.re), vadd(x2.re, x3.re));
+    X.im = vsub(vadd(X.im, x1.im), vadd(x2.im, x3.im));
+    st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(kTwoPi * kFmSc, X.im), vmul(p.r2_sc, X.re)});
+    if (p.g_acqs) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-        if (e < ne) {
-            cx<V> gy = czero<V>();
-            cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
-            cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
-            if (p.g_acqs) st_cx(p.g_acqs + acq_b + static_cast<size_t>(e) * nv * 2, v0, remod_inv(m[e], gy));
-            const cx<V> q = cmulc(gy, y[e]);
-            X.re = vfma(T.r[e].te, q.re, X.re);
-            X.im = vfma(T.r[e].te, q.im, X.im);
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const EchoRec R = T.r[e];
+                const Mod<V> m = modulator_rec<V, false>(R, phi_t, r2, zero);
+                cx<V> gy = czero<V>();
+                cmac(gy, R.pw_re, -R.pw_im, gw);
+                cmac(gy, R.pf_re, -R.pf_im, gf);
+                st_cx(p.g_acqs + acq_b + e * plane, v0, remod_inv(m, gy));
+            }
         }
     }
-    st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(kTwoPi * kFmSc, X.im), vmul(p.r2_sc, X.re)});
 }
 
 // =================================================================================================
@@ -578,6 +607,10 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
         chunk_ctr = 0;
         mbar_fence_init();
     }
+    // Programmatic dependent launch: everything above overlaps the tail of the kernel before this one in the stream
+    // (normally ig_gen_tables, which releases its dependents at once); nothing below may run before that kernel's
+    // writes are visible.  A no-op when the launch carried no such dependency.
+    grid_dependency_wait();
     __syncthreads();
     float loss_part = 0.f;
     constexpr int kConsumers = NCW * 32;
@@ -935,8 +968,17 @@ template <typename K> static int launch_tma(SolveParams p, cudaStream_t st, K ke
     const long tiles = static_cast<long>(p.nb) * ((p.nv + tile_vox - 1) / tile_vox);
     long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
     if (g > tiles) g = tiles;
-    kernel<<<static_cast<int>(g), threads, smem, st>>>(p, ma, mp);
-    IG_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(g));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    IG_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, ma, mp));
     return 0;
 }
 
@@ -1014,8 +1056,7 @@ extern "C" int ig_a2a_bwd(const float *acqs_d, const float *pm_d, long pm_bstrid
     SolveParams p{};
     p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
     p.flags = flags; p.g_rho = g_rho_d; p.g_shat = g_shat_d; p.g_acqs = g_acqs_d; p.g_pm = g_pm_d;
-    // the adjoint keeps y_e and the modulators of every echo live: one voxel per thread keeps it at two blocks per SM
-    const bool packed = false;
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, g_rho_d, g_shat_d, g_acqs_d, g_pm_d});
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;

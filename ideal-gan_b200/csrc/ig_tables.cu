@@ -140,6 +140,7 @@ __device__ __forceinline__ double half_warp_sum(double v) {
 // of the 320 floats of the table is written exactly once.
 constexpr int kTabWarps = 4;
 __global__ void __launch_bounds__(kTabWarps * 32) gen_tables_kernel(const float *__restrict__ te, int nb, int ne, float field, float *__restrict__ tab) {
+    grid_launch_dependents();          // a kernel launched behind this one with PDL may start its prologue now; it still waits for our writes
     const int b = blockIdx.x * kTabWarps + (threadIdx.x >> 5);
     if (b >= nb) return;
     const int lane = threadIdx.x & 31, e = lane & 15, half = lane >> 4;

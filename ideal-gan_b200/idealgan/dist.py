@@ -49,3 +49,53 @@ def gather_batch(tensor_shard, global_nb, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+class AsyncLossReducer:
+    """The objective's one collective, taken off the critical path ("pure latency ... overlap it with the
+    next micro-batch").  The scalar of step i is all-reduced asynchronously while the kernels of step i + 1 run: the
+    next step does not read it, so nothing on the compute stream has to wait.  `depth` scalars rotate; a slot is handed
+    out again only once its previous reduction has completed (with NCCL that is a stream-side wait, not a host wait).
+
+        red = AsyncLossReducer(device)
+        for step in ...:
+            loss = red.acquire()          # (1,) float32, to be overwritten by the loss kernel of this step
+            launch_kernels(..., loss)
+            red.submit()                  # starts the all-reduce of this step's scalar
+        red.drain()                       # before reading / timing: every outstanding reduction is ordered before what follows
+        red.last()                        # reduced scalar of the most recent step
+    """
+
+    def __init__(self, device, depth=2, group=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.group = group
+        self.bufs = [torch.zeros(1, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.pending = [None] * depth
+        self.step = -1
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def acquire(self):
+        self.step += 1
+        i = self.step % len(self.bufs)
+        if self.pending[i] is not None:
+            self.pending[i].wait()
+            self.pending[i] = None
+        return self.bufs[i]
+
+    def submit(self):
+        if self.step < 0:
+            raise RuntimeError("submit() before acquire()")
+        if self.active:
+            i = self.step % len(self.bufs)
+            self.pending[i] = dist.all_reduce(self.bufs[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def drain(self):
+        for i, w in enumerate(self.pending):
+            if w is not None:
+                w.wait()
+                self.pending[i] = None
+
+    def last(self):
+        self.drain()
+        return self.bufs[self.step % len(self.bufs)]

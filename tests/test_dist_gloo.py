@@ -76,3 +76,38 @@ def test_sharded_objective_equals_global_objective(world, nb):
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, nb, out), nprocs=world, join=True)
         assert dict(out) == {r: True for r in range(world)}
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        red = igdist.AsyncLossReducer(torch.device("cpu"), depth=2)
+        got = []
+        for step in range(5):
+            buf = red.acquire()
+            if step >= 2:                       # the slot handed out again holds the reduced scalar of step - 2
+                got.append((step - 2, float(buf.item())))
+            buf.fill_(float((rank + 1) * (step + 1)))          # this rank's local objective term of the step
+            red.submit()
+        last = float(red.last().item())
+        want = lambda st: float(sum((r + 1) * (st + 1) for r in range(world)))
+        out[rank] = all(abs(v - want(st)) < 1e-6 for st, v in got) and abs(last - want(4)) < 1e-6 and len(got) == 3
+    finally:
+        dist.destroy_process_group()
+
+
+def test_async_loss_reducer_overlaps_and_orders():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_reducer_worker, args=(2, port, out), nprocs=2, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_async_loss_reducer_single_process_is_a_no_op():
+    red = igdist.AsyncLossReducer(torch.device("cpu"), depth=3)
+    for step in range(4):
+        red.acquire().fill_(step + 1.0)
+        red.submit()
+    assert red.last().item() == 4.0

@@ -85,6 +85,8 @@ def main():
     add("ig_a2a_fwd", "acq_to_acq forward (rho + S_hat)", nb, nv, ne, 8 * ne + 8 + 16 + 8 * ne, lambda: ops.a2a_fwd(acqs, pm, tab))
     add("ig_a2a_bwd", "acq_to_acq adjoint (dPM only)", nb, nv, ne, 8 * ne + 8 + 8 * ne + 8,
         lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=False))
+    add("ig_a2a_bwd[+dS]", "acq_to_acq adjoint (dPM + dS)", nb, nv, ne, 8 * ne + 8 + 8 * ne + 8 + 8 * ne,
+        lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=True))
     add("ig_a2a_loss", "C2 fused objective (headline)", nb, nv, ne, 8 * ne + 8 + 8, lambda: ops.a2a_loss(acqs, pm, tab))
     add("ig_a2a_loss[+rho,S_hat]", "C2 fused + materialised outputs", nb, nv, ne, 8 * ne + 8 + 8 + 16 + 8 * ne,
         lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True))
@@ -103,7 +105,10 @@ def main():
     nv = H * W
     maps, te, tab, acqs = make(nb, H, W, ne, te_random=True)
     add("ig_ideal_fwd[wfpm]", "C3 per-sample TEs 256x192x192", nb, nv, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
-    add("ig_get_rho_fwd", "C3", nb, nv, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, maps[:, 2:3].contiguous(), tab))
+    pm3 = maps[:, 2:3].contiguous()
+    add("ig_get_rho_fwd", "C3", nb, nv, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm3, tab))
+    up3 = torch.randn((nb, 2, H, W, 2), device=dev)
+    add("ig_get_rho_bwd", "C3 (dPM + dS)", nb, nv, ne, 8 * ne + 8 + 16 + 8 * ne + 8, lambda: ops.get_rho_bwd(acqs, pm3, tab, up3, None))
     del maps, acqs
     torch.cuda.empty_cache()
     # C1: single slice latency
