@@ -42,6 +42,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so the real
+# stdout is set aside for that line and file descriptor 1 is pointed at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # clocks: sample NVML while the timed regions run
 # ---------------------------------------------------------------------------------------------------------------
@@ -156,7 +167,7 @@ def run_reference(args):
                        "algorithm is timed as the torch-CPU port held to the reference's vectors (tests/test_oracle_golden.py)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -338,7 +349,7 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -213,15 +213,44 @@ def a2a_loss(acqs, pm, tab, r2_sc=200.0, inv_n=None, want_rho=False, want_shat=F
     return loss, g_pm, rho, shat
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# second tier (ig_tier2.cu)
-# ---------------------------------------------------------------------------------------------------------------
 def _plane(t, name, nb, nv):
     """(nb, 1, H, W, 1)-like tensor -> contiguous (nb, nv) view."""
     t = _chk(t, name)
     if t.numel() != nb * nv:
         raise ValueError(f"{name}: expected {nb} x {nv} values, got shape {tuple(t.shape)}")
     return t.reshape(nb, nv)
+
+
+def a2a_uq_loss(acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc=200.0, inv_n=None, want_rho=False):
+    """Fused uncertainty-aware objective (ig_uq.cu).  phi_var / r2_mean / r2_var: (nb,1,H,W,1) moment maps in network units
+    (r2_mean = r2_var = None: rem_R2).  Returns (loss[1], g_pm (nb,1,H,W,2), g_phi_var, g_r2_mean | None, g_r2_var | None,
+    rho | None), the moment gradients shaped like their inputs."""
+    acqs, nb, ne, H, W = _acq_dims(acqs, False)
+    pm, stride = _pm_view(pm, nb, H, W, False)
+    if (r2_mean is None) != (r2_var is None):
+        raise ValueError("r2_mean and r2_var go together (both None = rem_R2)")
+    nv = H * W
+    pv = _plane(phi_var, "phi_var", nb, nv)
+    rm = None if r2_mean is None else _plane(r2_mean, "r2_mean", nb, nv)
+    rv = None if r2_var is None else _plane(r2_var, "r2_var", nb, nv)
+    inv_n = 1.0 / acqs.numel() if inv_n is None else inv_n
+    dev = acqs.device
+    g_pm = torch.empty((nb, 1, H, W, 2), dtype=torch.float32, device=dev)
+    g_pv = torch.empty(phi_var.shape, dtype=torch.float32, device=dev)
+    g_rm = None if rm is None else torch.empty(r2_mean.shape, dtype=torch.float32, device=dev)
+    g_rv = None if rv is None else torch.empty(r2_var.shape, dtype=torch.float32, device=dev)
+    rho = torch.empty((nb, 2, H, W, 2), dtype=torch.float32, device=dev) if want_rho else None
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    scr = loss_scratch(dev, nb, nv)
+    L.check(L.load().ig_a2a_uq_loss(acqs.data_ptr(), pm.data_ptr(), stride, pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv,
+                                    float(r2_sc), float(inv_n), g_pm.data_ptr(), g_pv.data_ptr(), _ptr(g_rm), _ptr(g_rv), _ptr(rho),
+                                    loss.data_ptr(), scr.data_ptr(), scr.numel(), _stream()), "ig_a2a_uq_loss")
+    return loss, g_pm, g_pv, g_rm, g_rv, rho
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second tier (ig_tier2.cu)
+# ---------------------------------------------------------------------------------------------------------------
 
 
 def eigenvals_fwd(X):

@@ -137,6 +137,44 @@ def physics_loss_a2a(acqs, pm, te, field=1.5, r2_sc=200.0, inv_n=None):
     return _A2ALoss.apply(acqs, pm, tab, float(r2_sc), inv_n)
 
 
+class _A2AUqLoss(torch.autograd.Function):
+    """Fused uncertainty-aware objective: forward produces every gradient, backward scales them."""
+
+    @staticmethod
+    def forward(ctx, acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n):
+        loss, g_pm, g_pv, g_rm, g_rv, rho = ops.a2a_uq_loss(acqs.contiguous(), pm.contiguous(), phi_var.contiguous(),
+                                                            None if r2_mean is None else r2_mean.contiguous(),
+                                                            None if r2_var is None else r2_var.contiguous(), tab, r2_sc, inv_n, want_rho=True)
+        if pm.shape[1] != 1:
+            full = torch.zeros_like(pm)
+            full[:, :1] = g_pm
+            g_pm = full
+        ctx.has_r2 = r2_mean is not None
+        ctx.save_for_backward(g_pm, g_pv, *([g_rm, g_rv] if ctx.has_r2 else []))
+        ctx.mark_non_differentiable(rho)
+        return loss.reshape(()), rho
+
+    @staticmethod
+    def backward(ctx, g, _g_rho):
+        saved = ctx.saved_tensors
+        g_rm, g_rv = (saved[2] * g, saved[3] * g) if ctx.has_r2 else (None, None)
+        return None, saved[0] * g, saved[1] * g, g_rm, g_rv, None, None, None
+
+
+def physics_loss_a2a_uq(acqs, pm, phi_var, r2_mean, r2_var, te, field=1.5, r2_sc=200.0, inv_n=None):
+    """The AI-DEAL training objective as one kernel (train-IDEAL-unsup.py:214-231): acq_to_acq -> mask ->
+    acq_uncertainty(stop_gradient(A2B_WF), FM, R2) -> VarMeanSquaredError.  `pm` is the (phi, R2*) sample fed to acq_to_acq,
+    `phi_var` / `r2_mean` / `r2_var` the `.variance()` / `.mean()` maps of the network's output distributions
+    ((nb,1,H,W,1); r2_mean = r2_var = None is rem_R2=True).  Differentiable in pm and the moment maps.
+    Returns (loss, A2B_WF) with A2B_WF = rho_hat / rho_sc detached, as the training loop logs it."""
+    tab, ne = _tables(te, field, acqs.device)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    if ne != acqs.shape[1]:
+        raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[1]}")
+    inv_n = 1.0 / acqs.numel() if inv_n is None else float(inv_n)
+    return _A2AUqLoss.apply(acqs, pm, phi_var, r2_mean, r2_var, tab, float(r2_sc), inv_n)
+
+
 class _IdealLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, maps, acqs, tab, model, r2_sc, flags, inv_n):

@@ -126,6 +126,17 @@ int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const f
                 float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
                 size_t scratch_bytes, void *stream);
 
+/* fused uncertainty-aware objective of the published AI-DEAL model (train-IDEAL-unsup.py:214-231; IDEAL_model.py:142-200,710-767;
+ * tf2gan/loss.py:130-140): acq_to_acq -> mask -> acq_uncertainty(stop_gradient(rho)) -> VarMeanSquaredError, with all gradients.
+ * phi_var_d / r2_mean_d / r2_var_d: (nb, nv) moment maps in network units (r2_* both NULL = rem_R2).
+ * loss_d[0] = inv_n * sum over (e, component) of [ (A - mask(S_hat))^2 / std_e + log std_e ], std_e = sqrt(max(var_e, 1e-5));
+ * g_pm_d (nb, nv, 2); g_phi_var_d / g_r2_mean_d / g_r2_var_d (nb, nv) (the r2 outputs may be NULL; zero-filled under rem_R2);
+ * rho_d optional (nb, 2, nv, 2) = rho_hat / rho_sc. */
+int ig_a2a_uq_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *phi_var_d, const float *r2_mean_d,
+                   const float *r2_var_d, const float *tab_d, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm_d,
+                   float *g_phi_var_d, float *g_r2_mean_d, float *g_r2_var_d, float *rho_d, float *loss_d, void *scratch_d,
+                   size_t scratch_bytes, void *stream);
+
 /* ---- second tier: magnitude fit, uncertainty propagation, PDFF (IDEAL_model.py:100-138,314-401,628-767) ---- */
 /* eigenvals: x_d (n, 3) = (a, b, c) -> xy_d (n, 2), ratio_d (n); adjoint with optional upstreams */
 int ig_eigenvals(const float *x_d, long n, float *xy_d, float *ratio_d, void *stream);

@@ -331,6 +331,41 @@ def gen_tier2():
     save("tier2", **out)
 
 
+def gen_uq():
+    """The UQ training objective of train-IDEAL-unsup.py:214-231 composed from the reference's own functions:
+    get_rho (= the A2B_WF its callers unpack from acq_to_acq), acq_to_acq, acq_uncertainty on the stop-gradient
+    estimate, VarMeanSquaredError."""
+    rng = np.random.default_rng(4)
+    out = {}
+    for name, nb, ne, field, rem in [("uq_orig6", 2, 6, 1.5, False), ("uq_rand5_rem", 2, 5, 1.5, True), ("uq_3T", 2, 6, 3.0, False)]:
+        maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+        te = synth.te_orig(nb, ne) if name == "uq_orig6" else synth.te_random(nb, ne, rng)
+        if field == 3.0:
+            te = (te * np.float32(0.5)).astype(np.float32)
+        with torch.no_grad():
+            acqs = synth.add_noise(N(wf.IDEAL_Layer(field=field)(T(maps), te=T(te))), rng)
+        acqs[0, 1, H // 2, W // 2, 0] = 0.0                                   # one ragged voxel: per-component mask
+        pm = (maps[:, 2:3] + 0.03 * rng.standard_normal(maps[:, 2:3].shape).astype(np.float32) * (maps[:, 2:3] != 0)).astype(np.float32)
+        tissue = (maps[:, 0:1, :, :, 0:1] != 0).astype(np.float32)
+        phi_v = (rng.uniform(1e-5, 4e-3, size=(nb, 1, H, W, 1)).astype(np.float32) * tissue)
+        r2_m = np.ascontiguousarray(pm[:, :, :, :, 1:2])
+        r2_v = (rng.uniform(1e-5, 3e-3, size=(nb, 1, H, W, 1)).astype(np.float32) * tissue)
+        a = T(acqs)
+        p, pv, rm, rv = T(pm, grad=True), T(phi_v, grad=True), T(r2_m, grad=True), T(r2_v, grad=True)
+        rho = wf.get_rho(a, p, field=field, te=T(te))
+        recon = wf.acq_to_acq(a, p, te=T(te), field=field)
+        recon = torch.where(a != 0.0, recon, torch.zeros_like(recon))
+        var = wf.acq_uncertainty(rho.detach(), Moments(None, pv), Moments(rm, rv), ne=ne, te=T(te), field=field, rem_R2=rem)
+        loss = ref_loss.VarMeanSquaredError()(a, tf_shim.concat([recon, var], axis=-1))
+        grads = torch.autograd.grad(loss, [p, pv, rm, rv], allow_unused=True)
+        g = [N(x) if x is not None else np.zeros(tuple(t.shape), np.float32) for x, t in zip(grads, [p, pv, rm, rv])]
+        out.update({f"{name}_acqs": acqs, f"{name}_te": te, f"{name}_field": np.float32(field), f"{name}_rem": np.bool_(rem),
+                    f"{name}_pm": pm, f"{name}_phi_v": phi_v, f"{name}_r2_m": r2_m, f"{name}_r2_v": r2_v,
+                    f"{name}_loss": np.float32(loss.item()), f"{name}_var": N(var), f"{name}_rho": N(rho),
+                    f"{name}_gpm": g[0], f"{name}_gphi_v": g[1], f"{name}_gr2_m": g[2], f"{name}_gr2_v": g[3]})
+    save("uq", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_tables()
@@ -338,3 +373,4 @@ if __name__ == "__main__":
     gen_solve()
     gen_losses()
     gen_tier2()
+    gen_uq()

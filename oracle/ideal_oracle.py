@@ -510,6 +510,21 @@ def physics_loss_a2a(acqs, param_maps, te=None, field=1.5, r2_sc=200.0, rdtype=t
     return masked_mse(acqs, recon), rho, recon
 
 
+def physics_loss_a2a_uq(acqs, param_maps, phi_var, r2_mean=None, r2_var=None, te=None, field=1.5, r2_sc=200.0,
+                        rdtype=torch.float32):
+    """The published AI-DEAL objective (train-IDEAL-unsup.py:214-231): acq_to_acq -> mask, signal variance from
+    acq_uncertainty on the STOP-GRADIENT water/fat estimate, VarMeanSquaredError on [recon, var].  `phi_var`, `r2_mean`,
+    `r2_var` are (nb,1,H,W,1) maps in network units (what `.variance()` / `.mean()` of the tfp outputs hold);
+    r2_mean = r2_var = None is rem_R2=True.  Returns (loss, rho_hat/rho_sc, S_hat unmasked, var)."""
+    acqs = _t(acqs, rdtype)
+    rho, recon = acq_to_acq(acqs, param_maps, te=te, field=field, r2_sc=r2_sc, rdtype=rdtype)
+    masked = torch.where(acqs != 0, recon, torch.zeros_like(recon))
+    rem = r2_mean is None
+    var = acq_uncertainty(rho.detach(), Moments(None, phi_var), None if rem else Moments(r2_mean, r2_var), ne=acqs.shape[1], te=te,
+                          r2_sc=r2_sc, field=field, rem_R2=rem, rdtype=rdtype)
+    return var_mse(acqs, torch.cat([masked, var], dim=-1)), rho, recon, var
+
+
 def physics_loss_fwd(acqs, out_maps, te, field=1.5, r2_sc=200.0, model="wfpm", rdtype=torch.float32):
     """Forward-model -> mask -> MSE objective (train-IDEAL-single.py:154-157 for model='magpha')."""
     fn = {"wfpm": IDEAL_model, "ffpd": IDEAL_mag, "magpha": IDEAL_mag_phase}[model]

@@ -226,6 +226,31 @@ def test_pdff_uncertainty(golden, name):
     assert_close(npy(rvar), g[name + "_rho_var"], 2e-5)
 
 
+@pytest.mark.parametrize("name", ["uq_orig6", "uq_rand5_rem", "uq_3T"])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_uq_objective(golden, name, rdtype, tol):
+    """train-IDEAL-unsup.py:214-231 composed from the reference's functions (oracle/gen_golden.py:gen_uq)."""
+    g = golden("uq")
+    rem = bool(g[name + "_rem"])
+    p, pv = tt(g[name + "_pm"], True, rdtype), tt(g[name + "_phi_v"], True, rdtype)
+    rm, rv = tt(g[name + "_r2_m"], True, rdtype), tt(g[name + "_r2_v"], True, rdtype)
+    loss, rho, _, var = orc.physics_loss_a2a_uq(tt(g[name + "_acqs"]), p, pv, None if rem else rm, None if rem else rv,
+                                                 te=tt(g[name + "_te"]), field=float(g[name + "_field"]), rdtype=rdtype)
+    # the objective sums ~log(std) terms of both signs: compare on the scale of its largest terms, like its gradients
+    assert abs(loss.item() - float(g[name + "_loss"])) <= 10 * tol * max(1.0, abs(float(g[name + "_loss"])))
+    assert_close(npy(rho), g[name + "_rho"], tol, "rho")
+    assert_close(npy(var), g[name + "_var"], 2e-5, "var")            # 1 - exp(-x), x ~ 1e-3, in the reference's fp32
+    grads = torch.autograd.grad(loss, [p, pv] + ([] if rem else [rm, rv]))
+    # gradients through 1/std^3 of fp32 variances: the reference's own rounding of var (2e-5) is amplified
+    assert_close(npy(grads[0]), g[name + "_gpm"], 1e-4, "grad pm")
+    assert_close(npy(grads[1]), g[name + "_gphi_v"], 1e-4, "grad phi var")
+    if not rem:
+        assert_close(npy(grads[2]), g[name + "_gr2_m"], 1e-4, "grad r2 mean")
+        assert_close(npy(grads[3]), g[name + "_gr2_v"], 1e-4, "grad r2 var")
+    else:
+        assert not g[name + "_gr2_m"].any() and not g[name + "_gr2_v"].any()
+
+
 def test_round_trip_and_idempotence():
     """SURVEY §8c KATs (i)-(iv) in fp64."""
     from idealgan import synth

@@ -90,6 +90,11 @@ def main():
     add("ig_a2a_loss", "C2 fused objective (headline)", nb, nv, ne, 8 * ne + 8 + 8, lambda: ops.a2a_loss(acqs, pm, tab))
     add("ig_a2a_loss[+rho,S_hat]", "C2 fused + materialised outputs", nb, nv, ne, 8 * ne + 8 + 8 + 16 + 8 * ne,
         lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True))
+    pv = torch.rand((nb, 1, H, W, 1), device=dev, generator=g) * 4e-3
+    rv = torch.rand((nb, 1, H, W, 1), device=dev, generator=g) * 3e-3
+    rm = pm[..., 1:2].contiguous()
+    add("ig_a2a_uq_loss", "AI-DEAL UQ objective (fused, all gradients)", nb, nv, ne, 8 * ne + 8 + 12 + 8 + 12,
+        lambda: ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab))
     # C4: bipolar mag/phase fused objective
     mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
     mp[:, 1] -= 0.25
