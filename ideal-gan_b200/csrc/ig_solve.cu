@@ -10,7 +10,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "ig_common.cuh"
+#include "ig_uq.cuh"
 
 namespace ig {
 
@@ -19,6 +19,8 @@ struct SolveParams {
     const float *g_rho, *g_demod, *g_shat;
     float *rho, *demod, *shat;
     float *g_acqs, *g_pm, *g_bip;
+    const float *phi_var, *r2_mean, *r2_var;       // uncertainty-aware objective: (nb, nv) moment maps (r2_* NULL = rem_R2)
+    float *g_phi_var, *g_r2_mean, *g_r2_var;
     float *loss;
     void *scratch;
     long pm_bstride, bip_bstride;
@@ -577,26 +579,30 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
 // to STAGES tiles per block are in flight to HBM.
 // =================================================================================================
 constexpr int kChunkVox = 64;                          // voxels per consumer-warp chunk (two per lane)
-template <int NE, int STAGES, int CH> struct TmaCfg {
+template <int NE, int STAGES, int CH, bool UQ = false> struct TmaCfg {
     static constexpr int tile_vox = CH * kChunkVox;                               // voxels per tile = per ring stage
     static constexpr int plane_bytes = tile_vox * 8;                              // one complex plane of a tile
     static constexpr int tab_bytes = NE * IG_REC_FLOATS * 4;                      // the sample's echo records ride along with the tile
-    static constexpr int stage_bytes = (NE + 1) * plane_bytes + ((tab_bytes + 127) / 128) * 128;
+    static constexpr int uq_off = (NE + 1) * plane_bytes + ((tab_bytes + 127) / 128) * 128;   // UQ: three real planes (phi_var, r2_mean, r2_var)
+    static constexpr int real_bytes = tile_vox * 4;
+    static constexpr int stage_bytes = uq_off + (UQ ? 3 * real_bytes : 0);
     static constexpr int smem_bytes = STAGES * stage_bytes;
 };
 
 // Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
 // cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
-template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE, int NCW, bool TMAP>
+template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE, int NCW, bool TMAP, bool UQ>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB)
 a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map_acq, const __grid_constant__ CUtensorMap map_pm) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ int2 stage_tile[STAGES];             // (sample, first voxel) of the tile in each stage; sample < 0 = end
     __shared__ int chunk_ctr;                       // consumer warps draw 64-voxel chunks of the ring from here
-    using Cfg = TmaCfg<NE, STAGES, CH>;
+    static_assert(!UQ || MODE == 1, "the uncertainty-aware objective lives in the register-resident path");
+    using Cfg = TmaCfg<NE, STAGES, CH, UQ>;
     constexpr int kTileVox = Cfg::tile_vox, kPlaneBytes = Cfg::plane_bytes;
     const int nv = p.nv, ne = EXACT ? NE : p.ne;
+    [[maybe_unused]] const bool rem = p.r2_mean == nullptr;
     const int tiles_ps = (nv + kTileVox - 1) / kTileVox;
     const int total = p.nb * tiles_ps;
     if (threadIdx.x == 0) {
@@ -652,7 +658,8 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                 stage_tile[s] = make_int2(b, vs);
                 // end marker: completes the phase without data
                 if (end) mbar_arrive(&full_bar[s]);
-                else mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + Cfg::tab_bytes);
+                else mbar_expect_tx(&full_bar[s], bytes * static_cast<uint32_t>(ne + 1) + Cfg::tab_bytes +
+                                                      (UQ ? static_cast<uint32_t>(nvox) * 4u * (rem ? 1u : 3u) : 0u));
             }
             __syncwarp();
             if (end) {
@@ -670,6 +677,15 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     bulk_g2s(stage + ne * kPlaneBytes, p.pm + b * p.pm_bstride + static_cast<size_t>(vs) * 2, bytes, &full_bar[s]);
                 }
                 bulk_g2s(stage + (NE + 1) * kPlaneBytes, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, Cfg::tab_bytes, &full_bar[s]);
+                if constexpr (UQ) {
+                    const size_t off = static_cast<size_t>(b) * nv + vs;
+                    const uint32_t rbytes = static_cast<uint32_t>(nvox) * 4u;
+                    bulk_g2s(stage + Cfg::uq_off, p.phi_var + off, rbytes, &full_bar[s]);
+                    if (!rem) {
+                        bulk_g2s(stage + Cfg::uq_off + Cfg::real_bytes, p.r2_mean + off, rbytes, &full_bar[s]);
+                        bulk_g2s(stage + Cfg::uq_off + 2 * Cfg::real_bytes, p.r2_var + off, rbytes, &full_bar[s]);
+                    }
+                }
             }
         }
     } else {
@@ -718,7 +734,22 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                         }
                     }
                     if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
-                        if (active) st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                        if (active) {
+                            st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                            if constexpr (UQ) {
+                                // rho = 0 -> var = 0 -> the floor: every (echo, component) contributes log sqrt(1e-5), no gradient
+                                loss_part += static_cast<float>(ne) * 2.0f * -11.512925464970229f;
+                                const size_t o = static_cast<size_t>(b) * nv;
+                                st_real(p.g_phi_var + o, v0, zero);
+                                if (p.g_r2_mean) st_real(p.g_r2_mean + o, v0, zero);
+                                if (p.g_r2_var) st_real(p.g_r2_var + o, v0, zero);
+                                if (p.rho) {
+                                    float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                                    st_cx(rho_b, v0, czero<pk>());
+                                    st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, czero<pk>());
+                                }
+                            }
+                        }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty_bar[s]);
                         continue;
@@ -726,13 +757,26 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     slow = true;
                 }
                 pk phi_t = zero, r2s = zero;                       // r2s = R2* in 1/s
+                [[maybe_unused]] pk s_phi = zero, mu = zero, s_r = zero;   // UQ: variances / mean in physical units
                 if (active) {
                     const float4 m4 = sraw[ne * kPlaneF4];
                     phi_t = mk(m4.x, m4.z);
                     r2s = vmul(r2_sc, mk(m4.y, m4.w));
+                    if constexpr (UQ) {
+                        const float2 *real = reinterpret_cast<const float2 *>(stage + Cfg::uq_off) + slot;
+                        pk t; t.d = real[0];
+                        s_phi = vmul(kFmSc * kFmSc, t);
+                        if (!rem) {
+                            t.d = real[Cfg::real_bytes / 8];
+                            mu = vmul(r2_sc, t);
+                            t.d = real[2 * Cfg::real_bytes / 8];
+                            s_r = vmul(r2_sc * r2_sc, t);
+                        }
+                    }
                 }
                 cx<pk> y[NE];
                 [[maybe_unused]] pk d2[MODE == 1 ? NE : 1];
+                [[maybe_unused]] UqAcc2 acc2{zero, zero, zero, zero};
                 cx<pk> rw = czero<pk>(), rf = czero<pk>(), tw = czero<pk>(), tf = czero<pk>();
                 if (!slow) {
                     AbsRange ar{3.0e38f, 0.f, 3.0e38f, 0.f};
@@ -766,9 +810,19 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                             const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
                             const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
                             const cx<pk> r{vsub(yhat.re, y[e].re), vsub(yhat.im, y[e].im)};
-                            const cx<pk> w{vmul(dd, r.re), vmul(dd, r.im)};
-                            lsum = vfma(w.re, r.re, lsum);
-                            lsum = vfma(w.im, r.im, lsum);
+                            cx<pk> w;
+                            if constexpr (UQ) {
+                                // residual weighted by 1 / std_e; the variance terms run lane by lane (rsqrt, lg2, ex2 on the SFU)
+                                const pk a2 = vfma(yhat.re, yhat.re, vmul(yhat.im, yhat.im));
+                                const pk msd = vmul(dd, vfma(r.re, r.re, vmul(r.im, r.im)));
+                                const pk inv_std = uq_echo(R.te, a2, msd, s_phi, mu, s_r, rem, acc2);
+                                const pk wgt = vmul(inv_std, dd);
+                                w = cx<pk>{vmul(wgt, r.re), vmul(wgt, r.im)};
+                            } else {
+                                w = cx<pk>{vmul(dd, r.re), vmul(dd, r.im)};
+                                lsum = vfma(w.re, r.re, lsum);
+                                lsum = vfma(w.im, r.im, lsum);
+                            }
                             const cx<pk> g{vfma(R.te, yhat.re, vneg(h.re)), vfma(R.te, yhat.im, vneg(h.im))};
                             K.re = vfma(w.re, g.re, K.re);
                             K.re = vfma(w.im, g.im, K.re);
@@ -777,17 +831,43 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                         }
                     }
                     if (active) {
-                        loss_part += hsum(lsum);
+                        if constexpr (!UQ) loss_part += hsum(lsum);
                         st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<pk>{vmul(-2.0f * kTwoPi * kFmSc * p.inv_n, K.im), vmul(-2.0f * r2_sc * p.inv_n, K.re)});
                     }
                 } else if (active) {
 #pragma unroll
                     for (int l = 0; l < 2; ++l) {
-                        float ls, gphi, gr2;
-                        a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
-                                                r2_sc, ls, gphi, gr2);
+                        float ls = 0.f, gphi, gr2;
+                        if constexpr (UQ) {
+                            cx<float> w1, f1;
+                            UqAcc a1{0.f, 0.f, 0.f, 0.f};
+                            uq_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l), lane_get(r2s, l),
+                                              lane_get(s_phi, l), lane_get(mu, l), lane_get(s_r, l), rem, r2_sc, a1, gphi, gr2, w1, f1);
+                            lane_set(acc2.g_sphi, l, a1.g_sphi); lane_set(acc2.g_mu, l, a1.g_mu); lane_set(acc2.g_sr, l, a1.g_sr);
+                            lane_set(acc2.loss, l, a1.loss);
+                            lane_set(rw.re, l, w1.re); lane_set(rw.im, l, w1.im);
+                            lane_set(rf.re, l, f1.re); lane_set(rf.im, l, f1.im);
+                        } else {
+                            a2a_loss_slow_voxel<NE>(T, p.acqs + static_cast<size_t>(b) * ne * nv * 2, ne, nv, v0 + l, lane_get(phi_t, l),
+                                                    lane_get(r2s, l), r2_sc, ls, gphi, gr2);
+                        }
                         loss_part += ls;
                         reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+                    }
+                }
+                if constexpr (UQ) {
+                    if (active) {
+                        loss_part += hsum(acc2.loss);
+                        const size_t o = static_cast<size_t>(b) * nv;
+                        st_real(p.g_phi_var + o, v0, vmul(kFmSc * kFmSc * p.inv_n, acc2.g_sphi));
+                        if (p.g_r2_mean) st_real(p.g_r2_mean + o, v0, rem ? zero : vmul(r2_sc * p.inv_n, acc2.g_mu));
+                        if (p.g_r2_var) st_real(p.g_r2_var + o, v0, rem ? zero : vmul(r2_sc * r2_sc * p.inv_n, acc2.g_sr));
+                        if (p.rho) {
+                            const float inv = 1.0f / kRhoSc;
+                            float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                            st_cx(rho_b, v0, cx<pk>{vmul(inv, rw.re), vmul(inv, rw.im)});
+                            st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<pk>{vmul(inv, rf.re), vmul(inv, rf.im)});
+                        }
                     }
                 }
             } else {
@@ -988,6 +1068,65 @@ static bool all_aligned(std::initializer_list<const void *> ps) {
     return true;
 }
 
+// Ring configuration of the fused objectives: two blocks per SM, 8 consumer warps + 1 producer warp each, 512-voxel tiles,
+// as many ring stages as fit the 227 KB of shared memory.  Measured alternatives (profiles/history_r01.md): smaller tiles, one
+// 17-warp block per SM, 10-12 consumer warps per block and batched tile claims are all slower.
+template <int NE, bool UQ> static int launch_a2a_ring(const SolveParams &p, cudaStream_t st) {
+    constexpr int kBudget = 216 * 1024;
+    const int nb = p.nb, ne = p.ne, nv = p.nv;
+    auto go = [&](auto st_c, auto minb_c, auto mode_c) {
+        constexpr int S = decltype(st_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
+        constexpr int C = 8, W = 8;
+        using Cfg = TmaCfg<NE, S, C, UQ>;
+        constexpr bool exact_ok = NE <= 8;
+        CUtensorMap ma{}, mp{};
+        // tensor maps need whole 128-voxel rows; otherwise the tile is fetched plane by plane with bulk copies
+        const bool tmap = nv % 128 == 0 && plane_tensor_map(&ma, p.acqs, nv, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, C / 2, ne) &&
+                          plane_tensor_map(&mp, p.pm, nv, nb, p.pm_bstride, C / 2, 1);
+        const bool exact = exact_ok && ne == NE;
+        if (tmap) {
+            if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+            return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        }
+        if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+    };
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    // up to 8 echoes y (and d^2) stay in registers between the two passes (95 registers at NE = 6, no spills);
+    // beyond that y is parked in the thread's own 16 bytes of the stage
+    if constexpr (NE <= 8) {
+        if (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{});
+        return go(I2{}, I2{}, I1{});
+    } else if constexpr (!UQ) {
+        if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{});
+        if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{});
+        return go(I3{}, I1{}, I0{});
+    } else {
+        set_error("uncertainty-aware ring kernel: more than 8 echoes");
+        return IG_E_UNSUPPORTED;
+    }
+}
+
+// Entry used by ig_uq.cu: the uncertainty-aware objective on the TMA ring.  IG_E_UNSUPPORTED = shape not covered (the caller
+// then runs its plain persistent kernel): needs <= 8 echoes and 128-voxel rows (16-byte bulk copies of the real planes).
+int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
+                     const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
+                     float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st) {
+    if (ne > 8 || nv % 128 != 0 || pm_bstride % 4 != 0 ||
+        !all_aligned({acqs, pm, phi_var, r2_mean, r2_var, g_pm, g_phi_var, g_r2_mean, g_r2_var, rho}))
+        return IG_E_UNSUPPORTED;
+    SolveParams p{};
+    p.acqs = acqs; p.pm = pm; p.pm_bstride = pm_bstride; p.tab = tab; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.inv_n = inv_n;
+    p.g_pm = g_pm; p.rho = rho; p.loss = loss; p.scratch = scratch;
+    p.phi_var = phi_var; p.r2_mean = r2_mean; p.r2_var = r2_var; p.g_phi_var = g_phi_var; p.g_r2_mean = g_r2_mean; p.g_r2_var = g_r2_var;
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if constexpr (NE <= 8) return launch_a2a_ring<NE, true>(p, st);
+        else return static_cast<int>(IG_E_UNSUPPORTED);
+    });
+}
+
 }  // namespace ig
 
 using namespace ig;
@@ -1080,37 +1219,7 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
-        if (packed) {
-            // Two blocks per SM, 8 consumer warps + 1 producer warp each, 512-voxel tiles, as many ring stages as fit the
-            // 227 KB of shared memory.  Measured alternatives (profiles/history_r01.md): smaller tiles, one 17-warp block per
-            // SM, 10-12 consumer warps per block and batched tile claims are all slower.
-            constexpr int kBudget = 216 * 1024;
-            auto go = [&](auto st_c, auto minb_c, auto mode_c) {
-                constexpr int S = decltype(st_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
-                constexpr int C = 8, W = 8;
-                using Cfg = TmaCfg<NE, S, C>;
-                constexpr bool exact_ok = NE <= 8;
-                CUtensorMap ma{}, mp{};
-                // tensor maps need whole 128-voxel rows; otherwise the tile is fetched plane by plane with bulk copies
-                const bool tmap = nv % 128 == 0 && plane_tensor_map(&ma, acqs_d, nv, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, C / 2, ne) &&
-                                  plane_tensor_map(&mp, pm_d, nv, nb, pm_bstride, C / 2, 1);
-                const bool exact = exact_ok && ne == NE;
-                if (tmap) {
-                    if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-                    return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-                }
-                if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-                return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-            };
-            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-            using I3 = std::integral_constant<int, 3>;
-            // up to 8 echoes y (and d^2) stay in registers between the two passes (95 registers at NE = 6, no spills);
-            // beyond that y is parked in the thread's own 16 bytes of the stage
-            if constexpr (NE <= 8) return go(I3{}, I2{}, I1{});
-            if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{});
-            if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{});
-            return go(I3{}, I1{}, I0{});
-        }
+        if (packed) return launch_a2a_ring<NE, false>(p, st);
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
 }

@@ -11,7 +11,7 @@
 // The gradient w.r.t. (phi~, R~) is the MSE objective's with the residual weighted by 1/std_e (see ig_solve.cu); the
 // gradients w.r.t. the moment maps follow from d loss / d var_e = [var_e >= 1e-5] (1 - msd_e / (2 std_e)) / var_e.
 // Voxels with some, but not all, components exactly zero take the reference's per-component mask on a scalar path.
-#include "ig_common.cuh"
+#include "ig_uq.cuh"
 
 namespace ig {
 
@@ -23,97 +23,6 @@ struct UqParams {
     int nb, ne, nv;
     float r2_sc, inv_n;
 };
-
-constexpr float kVarFloor = 1e-5f;      // tf2gan/loss.py:135
-constexpr float kLn2 = 0.6931471805599453f;
-
-// 1 - e^{-x}, x >= 0, without the cancellation the reference's fp32 `1 - exp(-x)` suffers at x ~ 1e-3 (its own error
-// there is ~1e-4 relative); also returns e^{-x}
-__device__ __forceinline__ float one_minus_exp_neg(float x, float &e) {
-    e = fast_ex2(-x * kLog2e);
-    if (x < 0.25f) {
-        // x - x^2/2 + x^3/6 - ... (7 terms: relative error < 1e-7 below 0.25)
-        float s = fmaf(x, -1.0f / 5040.0f, 1.0f / 720.0f);
-        s = fmaf(x, -s, 1.0f / 120.0f);
-        s = fmaf(x, -s, 1.0f / 24.0f);
-        s = fmaf(x, -s, 1.0f / 6.0f);
-        s = fmaf(x, -s, 0.5f);
-        s = fmaf(x, -s, 1.0f);
-        return x * s;
-    }
-    return 1.0f - e;
-}
-
-// per-echo uncertainty terms of one voxel: variance, its floor gate, 1/std, and the accumulation of the moment gradients
-struct UqAcc {
-    float g_sphi, g_mu, g_sr, loss;
-};
-__device__ __forceinline__ float uq_echo(float te, float a2, float msd, float s_phi, float mu, float s_r, bool rem, UqAcc &acc) {
-    const float k = kTwoPi * te, k2 = k * k;
-    float ephi;
-    const float vphi = one_minus_exp_neg(k2 * s_phi, ephi);
-    const float er = rem ? 0.f : fast_ex2(-te * mu * kLog2e) * te * te;
-    const float var = fmaf(er, s_r, vphi) * a2;
-    const bool gate = var >= kVarFloor;
-    const float varc = gate ? var : kVarFloor;
-    const float inv_std = rsqrtf(varc);
-    float lg;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(varc));
-    acc.loss += fmaf(msd, inv_std, lg * kLn2);
-    const float gv = gate ? inv_std * inv_std * fmaf(-0.5f * msd, inv_std, 1.0f) : 0.f;
-    const float ga = gv * a2;
-    acc.g_sphi = fmaf(ga * k2, ephi, acc.g_sphi);
-    acc.g_mu = fmaf(-ga * te, er * s_r, acc.g_mu);
-    acc.g_sr = fmaf(ga, er, acc.g_sr);
-    return inv_std;
-}
-
-// scalar path with the per-component mask (train-IDEAL-unsup.py:218) and the general adjoint of acq_to_acq
-template <int NE>
-__device__ __forceinline__ void uq_slow_voxel(const SampleTab<NE> &T, const float *acq_b, int ne, int nv, int v, float phi_t, float r2, float s_phi,
-                                              float mu, float s_r, bool rem, float r2_sc, UqAcc &acc, float &gphi, float &gr2, cx<float> &rw,
-                                              cx<float> &rf) {
-    cx<float> y[NE];
-    Mod<float> m[NE];
-    rw = czero<float>();
-    rf = czero<float>();
-#pragma unroll 1
-    for (int e = 0; e < ne; ++e) {
-        m[e] = modulator(T, e, phi_t, r2, 0.f);
-        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
-        y[e] = demod(m[e], cx<float>{s.x, s.y});
-        cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y[e]);
-        cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y[e]);
-    }
-    cx<float> gw = czero<float>(), gf = czero<float>(), X = czero<float>();
-#pragma unroll 1
-    for (int e = 0; e < ne; ++e) {
-        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
-        const cx<float> yhat = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
-        const cx<float> sh = remod(m[e], yhat);
-        const cx<float> E{mask_sub(sh.re, s.x), mask_sub(sh.im, s.y)};
-        const float msd = E.re * E.re + E.im * E.im;
-        const float inv_std = uq_echo(T.r[e].te, yhat.re * yhat.re + yhat.im * yhat.im, msd, s_phi, mu, s_r, rem, acc);
-        const cx<float> vv = demod_fwd(m[e], cx<float>{inv_std * E.re, inv_std * E.im});
-        gw.re += vv.re;
-        gw.im += vv.im;
-        cmac(gf, T.r[e].c_re, -T.r[e].c_im, vv);
-        const cx<float> q = cmulc(vv, yhat);
-        X.re = fmaf(-T.r[e].te, q.re, X.re);
-        X.im = fmaf(-T.r[e].te, q.im, X.im);
-    }
-#pragma unroll 1
-    for (int e = 0; e < ne; ++e) {
-        cx<float> gy = czero<float>();
-        cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
-        cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
-        const cx<float> q = cmulc(gy, y[e]);
-        X.re = fmaf(T.r[e].te, q.re, X.re);
-        X.im = fmaf(T.r[e].te, q.im, X.im);
-    }
-    gphi = kTwoPi * kFmSc * X.im;      // caller applies 2 / N
-    gr2 = r2_sc * X.re;
-}
 
 // a voxel is "ragged" iff some but not all of its 2 ne components are exactly zero
 __device__ __forceinline__ void zero_range(float &lo, float &hi, float re, float im) {
@@ -293,6 +202,11 @@ extern "C" int ig_a2a_uq_loss(const float *acqs_d, const float *pm_d, long pm_bs
                           static_cast<const void *>(g_phi_var_d), static_cast<const void *>(g_r2_mean_d), static_cast<const void *>(g_r2_var_d)})
         packed = packed && (!q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        const int rc = a2a_uq_loss_ring(acqs_d, pm_d, pm_bstride, phi_var_d, r2_mean_d, r2_var_d, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d,
+                                        g_phi_var_d, g_r2_mean_d, g_r2_var_d, rho_d, loss_d, scratch_d, st);
+        if (rc != IG_E_UNSUPPORTED) return rc;
+    }
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         int grid = 1;

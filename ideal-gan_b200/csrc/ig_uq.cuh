@@ -1,0 +1,140 @@
+// Device helpers of the uncertainty-aware objective shared by the plain persistent kernel (ig_uq.cu) and the
+// TMA-pipelined one (ig_solve.cu).  See ig_uq.cu for the math and the reference lines.
+#pragma once
+#include "ig_common.cuh"
+
+namespace ig {
+
+constexpr float kVarFloor = 1e-5f;      // tf2gan/loss.py:135
+constexpr float kLn2 = 0.6931471805599453f;
+
+// 1 - e^{-x}, x >= 0, without the cancellation the reference's fp32 `1 - exp(-x)` suffers at x ~ 1e-3 (its own error
+// there is ~1e-4 relative); also returns e^{-x}
+__device__ __forceinline__ float one_minus_exp_neg(float x, float &e) {
+    e = fast_ex2(-x * kLog2e);
+    if (x < 0.25f) {
+        // x - x^2/2 + x^3/6 - ... (7 terms: relative error < 1e-7 below 0.25)
+        float s = fmaf(x, -1.0f / 5040.0f, 1.0f / 720.0f);
+        s = fmaf(x, -s, 1.0f / 120.0f);
+        s = fmaf(x, -s, 1.0f / 24.0f);
+        s = fmaf(x, -s, 1.0f / 6.0f);
+        s = fmaf(x, -s, 0.5f);
+        s = fmaf(x, -s, 1.0f);
+        return x * s;
+    }
+    return 1.0f - e;
+}
+
+// per-echo uncertainty terms of one voxel: variance, its floor gate, 1/std, and the accumulation of the moment gradients
+struct UqAcc {
+    float g_sphi, g_mu, g_sr, loss;
+};
+__device__ __forceinline__ float uq_echo(float te, float a2, float msd, float s_phi, float mu, float s_r, bool rem, UqAcc &acc) {
+    const float k = kTwoPi * te, k2 = k * k;
+    float ephi;
+    const float vphi = one_minus_exp_neg(k2 * s_phi, ephi);
+    const float er = rem ? 0.f : fast_ex2(-te * mu * kLog2e) * te * te;
+    const float var = fmaf(er, s_r, vphi) * a2;
+    const bool gate = var >= kVarFloor;
+    const float varc = gate ? var : kVarFloor;
+    const float inv_std = rsqrtf(varc);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(varc));
+    acc.loss += fmaf(msd, inv_std, lg * kLn2);
+    const float gv = gate ? inv_std * inv_std * fmaf(-0.5f * msd, inv_std, 1.0f) : 0.f;
+    const float ga = gv * a2;
+    acc.g_sphi = fmaf(ga * k2, ephi, acc.g_sphi);
+    acc.g_mu = fmaf(-ga * te, er * s_r, acc.g_mu);
+    acc.g_sr = fmaf(ga, er, acc.g_sr);
+    return inv_std;
+}
+
+// the same for the two packed voxels of a lane pair: FP32 work as f32x2 instructions, transcendentals per lane on the SFU
+struct UqAcc2 {
+    pk g_sphi, g_mu, g_sr, loss;
+};
+__device__ __forceinline__ pk uq_echo(float te, pk a2, pk msd, pk s_phi, pk mu, pk s_r, bool rem, UqAcc2 &acc) {
+    const float k = kTwoPi * te, k2 = k * k;
+    const pk x = vmul(k2, s_phi);
+    const pk ephi = fast_ex2(vmul(-kLog2e, x));
+    // 1 - e^{-x}: series below 0.25 (see one_minus_exp_neg), 1 - e above
+    pk s = vfma(x, splat<pk>(-1.0f / 5040.0f), splat<pk>(1.0f / 720.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 120.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 24.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 6.0f));
+    s = vfma(vneg(x), s, splat<pk>(0.5f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f));
+    const pk series = vmul(x, s), direct = vsub(splat<pk>(1.0f), ephi);
+    const pk vphi = mk(x.d.x < 0.25f ? series.d.x : direct.d.x, x.d.y < 0.25f ? series.d.y : direct.d.y);
+    pk er = splat<pk>(0.f);
+    if (!rem) er = vmul(te * te, fast_ex2(vmul(-te * kLog2e, mu)));
+    const pk var = vmul(vfma(er, s_r, vphi), a2);
+    const bool g0 = var.d.x >= kVarFloor, g1 = var.d.y >= kVarFloor;
+    const pk varc = mk(g0 ? var.d.x : kVarFloor, g1 ? var.d.y : kVarFloor);
+    const pk inv_std = mk(rsqrtf(varc.d.x), rsqrtf(varc.d.y));
+    float l0, l1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(varc.d.x));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(varc.d.y));
+    acc.loss = vadd(acc.loss, vfma(msd, inv_std, vmul(kLn2, mk(l0, l1))));
+    pk gv = vmul(vmul(inv_std, inv_std), vfma(vmul(-0.5f, msd), inv_std, splat<pk>(1.0f)));
+    gv = mk(g0 ? gv.d.x : 0.f, g1 ? gv.d.y : 0.f);
+    const pk ga = vmul(gv, a2);
+    acc.g_sphi = vfma(vmul(k2, ga), ephi, acc.g_sphi);
+    acc.g_mu = vfma(vmul(-te, ga), vmul(er, s_r), acc.g_mu);
+    acc.g_sr = vfma(ga, er, acc.g_sr);
+    return inv_std;
+}
+
+// scalar path with the per-component mask (train-IDEAL-unsup.py:218) and the general adjoint of acq_to_acq
+template <int NE>
+__device__ __forceinline__ void uq_slow_voxel(const SampleTab<NE> &T, const float *acq_b, int ne, int nv, int v, float phi_t, float r2, float s_phi,
+                                              float mu, float s_r, bool rem, float r2_sc, UqAcc &acc, float &gphi, float &gr2, cx<float> &rw,
+                                              cx<float> &rf) {
+    cx<float> y[NE];
+    Mod<float> m[NE];
+    rw = czero<float>();
+    rf = czero<float>();
+#pragma unroll 1
+    for (int e = 0; e < ne; ++e) {
+        m[e] = modulator(T, e, phi_t, r2, 0.f);
+        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
+        y[e] = demod(m[e], cx<float>{s.x, s.y});
+        cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y[e]);
+        cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y[e]);
+    }
+    cx<float> gw = czero<float>(), gf = czero<float>(), X = czero<float>();
+#pragma unroll 1
+    for (int e = 0; e < ne; ++e) {
+        const float2 s = reinterpret_cast<const float2 *>(acq_b + static_cast<size_t>(e) * nv * 2)[v];
+        const cx<float> yhat = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
+        const cx<float> sh = remod(m[e], yhat);
+        const cx<float> E{mask_sub(sh.re, s.x), mask_sub(sh.im, s.y)};
+        const float msd = E.re * E.re + E.im * E.im;
+        const float inv_std = uq_echo(T.r[e].te, yhat.re * yhat.re + yhat.im * yhat.im, msd, s_phi, mu, s_r, rem, acc);
+        const cx<float> vv = demod_fwd(m[e], cx<float>{inv_std * E.re, inv_std * E.im});
+        gw.re += vv.re;
+        gw.im += vv.im;
+        cmac(gf, T.r[e].c_re, -T.r[e].c_im, vv);
+        const cx<float> q = cmulc(vv, yhat);
+        X.re = fmaf(-T.r[e].te, q.re, X.re);
+        X.im = fmaf(-T.r[e].te, q.im, X.im);
+    }
+#pragma unroll 1
+    for (int e = 0; e < ne; ++e) {
+        cx<float> gy = czero<float>();
+        cmac(gy, T.r[e].pw_re, -T.r[e].pw_im, gw);
+        cmac(gy, T.r[e].pf_re, -T.r[e].pf_im, gf);
+        const cx<float> q = cmulc(gy, y[e]);
+        X.re = fmaf(T.r[e].te, q.re, X.re);
+        X.im = fmaf(T.r[e].te, q.im, X.im);
+    }
+    gphi = kTwoPi * kFmSc * X.im;      // caller applies 2 / N
+    gr2 = r2_sc * X.re;
+}
+
+// host: the same objective on the TMA ring of ig_solve.cu (IG_E_UNSUPPORTED when the shape is not covered)
+int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
+                     const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
+                     float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st);
+
+}  // namespace ig

@@ -272,7 +272,7 @@ def test_uq_objective_vs_reference_vectors(golden, name):
         assert_close(host(g_rv), g[name + "_gr2_v"], 1e-4, "grad r2 var")
 
 
-@pytest.mark.parametrize("hw", [(9, 7), (48, 64)])
+@pytest.mark.parametrize("hw", [(9, 7), (48, 64), (40, 48), (30, 34)])     # scalar / TMA ring / ring with a ragged tile / plain packed kernel
 @pytest.mark.parametrize("ne", [3, 6, 12])
 def test_uq_objective_vs_fp64_oracle(hw, ne):
     """Same objective against the fp64 restatement on seeded inputs (scalar and packed kernels, ragged voxels)."""
