@@ -57,6 +57,10 @@ SIGNATURES = {
     "ig_acq_unc_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
     "ig_pdff_unc": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp]),
     "ig_pdff_extract": (_i, [_fp, _i, _i, _i, _fp, _fp]),
+    "ig_acq_to_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
+    "ig_acq_from_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
+    "ig_maps_to_flat": (_i, [_fp, _i, _i, _i, _i, _f, _fp, _fp]),
+    "ig_maps_from_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
     "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),
     "ig_ctx_destroy": (None, [C.c_void_p]),
     "ig_a2a_loss_host": (_i, [C.c_void_p, _fp, _fp, _fp, _i, _f, _f, _f, _fp, _fp]),

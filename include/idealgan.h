@@ -162,6 +162,17 @@ int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const float *phi_v
 /* PDFF maps from rho (nb,2,nv,2): mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|), 2 magnitude-discriminated; 0/0 -> 0 */
 int ig_pdff_extract(const float *rho_d, int nb, int nv, int mode, float *out_d, void *stream);
 
+/* ---- layout adapters: data.A_from_MEBCRN / B_from_MEBCRN / B_to_MEBCRN (data.py:262-329) ------------ */
+/* acquisitions (nb, ne, nv, 2) <-> channel-interleaved (nb, nv, 2 ne); the second is the adjoint (and inverse) of the first */
+int ig_acq_to_flat(const float *acqs_d, int nb, int ne, int nv, float *flat_d, void *stream);
+int ig_acq_from_flat(const float *flat_d, int nb, int ne, int nv, float *acqs_d, void *stream);
+/* B_from_MEBCRN.  mode 0: maps (nb,3,nv,2) -> (nb,nv,6) = (W_re, W_im, F_re, F_im, R2*, phi).
+ * mode 1 (mag_and_phase=True): maps (nb,2,nv,ch) -> (nb,nv,4 + 2 (ch - 2)), phase = c_pha * pi * maps[:,1,:,1]. */
+int ig_maps_to_flat(const float *maps_d, int nb, int nv, int mode, int ch, float c_pha, float *flat_d, void *stream);
+/* B_to_MEBCRN.  mode 0 'All' (nb,nv,6) -> (nb,3,nv,2); 1 'WF-PM' (nb,nv,4) -> (nb,3,nv,2); 2 'WF' (nb,nv,2) -> (nb,2,nv,2);
+ * 3 'PM' (nb,nv,2) -> (nb,1,nv,2). */
+int ig_maps_from_flat(const float *flat_d, int nb, int nv, int mode, float *maps_d, void *stream);
+
 /* ---- host-buffer pipeline (the call timed as `e2e` by bench.py) -------------------------------- */
 /* A context owns device staging buffers and streams on `device`; chunks of `chunk_nb` samples are copied
  * host->device, processed and copied back with copy/compute overlap.  Host buffers should be pinned. */

@@ -366,6 +366,43 @@ def gen_uq():
     save("uq", **out)
 
 
+def _reference_data_functions(names):
+    """data.py cannot be imported here (h5py, pydicom, nibabel, skimage are absent), so the SOURCE of the named top-level
+    functions is cut out of /root/reference/data.py with `ast` and executed unmodified against the shim."""
+    import ast
+    src = open(os.path.join(REF, "data.py")).read()
+    ns = {"tf": tf_shim, "np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, "data.py"), "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def gen_layout():
+    """data.A_from_MEBCRN / B_from_MEBCRN / B_to_MEBCRN (data.py:262-329)."""
+    A_from, B_from, B_to = _reference_data_functions(["A_from_MEBCRN", "B_from_MEBCRN", "B_to_MEBCRN"])
+    rng = np.random.default_rng(5)
+    out = {}
+    for ne in (3, 6):
+        a = rng.standard_normal((2, ne, H, W, 2)).astype(np.float32)
+        out[f"a{ne}_in"] = a
+        out[f"a{ne}_flat"] = N(A_from(T(a)))
+    b = rng.standard_normal((2, 3, H, W, 2)).astype(np.float32)
+    out["b_in"] = b
+    out["b_flat"] = N(B_from(T(b)))
+    for ch in (3, 4):
+        bm = rng.uniform(-0.5, 0.5, size=(2, 2, H, W, ch)).astype(np.float32)
+        out[f"bmp{ch}_in"] = bm
+        out[f"bmp{ch}_flat"] = N(B_from(T(bm), mag_and_phase=True))
+        out[f"bmp{ch}_flat_c1"] = N(B_from(T(bm), mag_and_phase=True, c_pha=1))
+    for mode, c in (("All", 6), ("WF-PM", 4), ("WF", 2), ("PM", 2)):
+        f = rng.standard_normal((2, H, W, c)).astype(np.float32)
+        key = mode.replace("-", "")
+        out[f"to_{key}_in"] = f
+        out[f"to_{key}_out"] = N(B_to(T(f), mode=mode))
+    save("layout", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_tables()
@@ -374,3 +411,4 @@ if __name__ == "__main__":
     gen_losses()
     gen_tier2()
     gen_uq()
+    gen_layout()

@@ -550,6 +550,44 @@ def pdff_extract(rho, mode="complex_sum"):
     return torch.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
 
 
+# ----------------------------------------------------------------------------------------------
+# layout adapters (data.py:262-329)
+# ----------------------------------------------------------------------------------------------
+def A_from_MEBCRN(A):
+    """(nb, ne, H, W, 2) -> (nb, H, W, 2 ne), Re/Im interleaved per echo (data.py:262-276)."""
+    nb, ne, H, W, _ = A.shape
+    return A.permute(0, 2, 3, 1, 4).reshape(nb, H, W, 2 * ne)
+
+
+def A_to_MEBCRN(F):
+    nb, H, W, c = F.shape
+    return F.reshape(nb, H, W, c // 2, 2).permute(0, 3, 1, 2, 4)
+
+
+def B_from_MEBCRN(B, mag_and_phase=False, c_pha=3):
+    """data.py:279-299.  The mag/phase branch rotates BOTH species by c_pha * pi * B[:, 1, ..., 1]."""
+    if mag_and_phase:
+        ang = c_pha * B[:, 1, :, :, 1:2] * np.pi
+        c, s = torch.cos(ang), torch.sin(ang)
+        return torch.cat([B[:, 0, :, :, :1] * c, B[:, 0, :, :, :1] * s, B[:, 0, :, :, 1:2] * c, B[:, 0, :, :, 1:2] * s,
+                          B[:, 0, :, :, 2:], B[:, 1, :, :, 2:]], dim=-1)
+    return torch.cat([B[:, 0], B[:, 1], B[:, 2, :, :, 1:], B[:, 2, :, :, :1]], dim=-1)
+
+
+def B_to_MEBCRN(B, mode="All"):
+    """data.py:302-329."""
+    z = torch.zeros_like(B[..., :1])
+    if mode == "WF":
+        return torch.stack([torch.cat([B[..., :1], z], -1), torch.cat([B[..., 1:], z], -1)], dim=1)
+    if mode == "PM":
+        return torch.cat([B[..., 1:], B[..., :1]], -1).unsqueeze(1)
+    if mode == "WF-PM":
+        return torch.stack([torch.cat([B[..., :1], z], -1), torch.cat([B[..., 1:2], z], -1), torch.cat([B[..., 3:], B[..., 2:3]], -1)], dim=1)
+    if mode == "All":
+        return torch.stack([B[..., :2], B[..., 2:4], torch.cat([B[..., 5:], B[..., 4:5]], -1)], dim=1)
+    raise ValueError(mode)
+
+
 def num_threads():
     return torch.get_num_threads()
 

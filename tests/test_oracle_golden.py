@@ -251,6 +251,22 @@ def test_uq_objective(golden, name, rdtype, tol):
         assert not g[name + "_gr2_m"].any() and not g[name + "_gr2_v"].any()
 
 
+def test_layout_adapters(golden):
+    """data.py:262-329 (oracle/gen_golden.py:gen_layout runs the reference's own function source): pure data movement."""
+    g = golden("layout")
+    for ne in (3, 6):
+        flat = orc.A_from_MEBCRN(tt(g[f"a{ne}_in"]))
+        assert np.array_equal(npy(flat), g[f"a{ne}_flat"])
+        assert np.array_equal(npy(orc.A_to_MEBCRN(flat)), g[f"a{ne}_in"])
+    assert np.array_equal(npy(orc.B_from_MEBCRN(tt(g["b_in"]))), g["b_flat"])
+    for ch in (3, 4):
+        assert_close(npy(orc.B_from_MEBCRN(tt(g[f"bmp{ch}_in"]), mag_and_phase=True)), g[f"bmp{ch}_flat"], 1e-6)
+        assert_close(npy(orc.B_from_MEBCRN(tt(g[f"bmp{ch}_in"]), mag_and_phase=True, c_pha=1)), g[f"bmp{ch}_flat_c1"], 1e-6)
+    for mode in ("All", "WF-PM", "WF", "PM"):
+        key = mode.replace("-", "")
+        assert np.array_equal(npy(orc.B_to_MEBCRN(tt(g[f"to_{key}_in"]), mode=mode)), g[f"to_{key}_out"])
+
+
 def test_round_trip_and_idempotence():
     """SURVEY §8c KATs (i)-(iv) in fp64."""
     from idealgan import synth

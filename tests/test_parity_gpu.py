@@ -301,6 +301,39 @@ def test_uq_objective_vs_fp64_oracle(hw, ne):
         assert_close(host(got), host(want.float()), 2e-5, "grad " + what)
 
 
+def test_layout_adapters_vs_reference_vectors(golden):
+    """data.A_from_MEBCRN / B_from_MEBCRN / B_to_MEBCRN: bit-exact data movement (the mag/phase branch: 1e-6, it has a sincos)."""
+    from idealgan import layout
+    g = golden("layout")
+    for ne in (3, 6):
+        flat = layout.A_from_MEBCRN(dev(g[f"a{ne}_in"]))
+        assert np.array_equal(host(flat), g[f"a{ne}_flat"])
+        assert np.array_equal(host(layout.A_to_MEBCRN(flat)), g[f"a{ne}_in"])
+    assert np.array_equal(host(layout.B_from_MEBCRN(dev(g["b_in"]))), g["b_flat"])
+    for ch in (3, 4):
+        assert_close(host(layout.B_from_MEBCRN(dev(g[f"bmp{ch}_in"]), mag_and_phase=True)), g[f"bmp{ch}_flat"], 1e-6)
+        assert_close(host(layout.B_from_MEBCRN(dev(g[f"bmp{ch}_in"]), mag_and_phase=True, c_pha=1)), g[f"bmp{ch}_flat_c1"], 1e-6)
+    for mode in ("All", "WF-PM", "WF", "PM"):
+        key = mode.replace("-", "")
+        assert np.array_equal(host(layout.B_to_MEBCRN(dev(g[f"to_{key}_in"]), mode=mode)), g[f"to_{key}_out"])
+    with pytest.raises(ValueError):
+        layout.B_to_MEBCRN(dev(g["to_All_in"]), mode="WF")
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 9, 7), (2, 6, 384, 384), (1, 16, 33, 65), (2, 1, 40, 40)])
+def test_acq_relayout_round_trip_and_adjoint(shape):
+    """Ragged tiles, every echo count class, BASELINE-size slices; autograd backward is the inverse adapter."""
+    from idealgan import layout
+    nb, ne, H, W = shape
+    a = torch.randn((nb, ne, H, W, 2), device="cuda", requires_grad=True)
+    flat = layout.A_from_MEBCRN(a)
+    assert torch.equal(flat, orc.A_from_MEBCRN(a.detach()))
+    assert torch.equal(layout.A_to_MEBCRN(flat.detach()), a.detach())
+    up = torch.randn_like(flat)
+    (ga,) = torch.autograd.grad((flat * up).sum(), [a])
+    assert torch.equal(ga, orc.A_to_MEBCRN(up).contiguous())
+
+
 def test_full_size_properties():
     """BASELINE-size slices (384 x 384 x 6): size-independent properties instead of an oracle run."""
     rng = np.random.default_rng(1234)

@@ -95,6 +95,14 @@ def main():
     rm = pm[..., 1:2].contiguous()
     add("ig_a2a_uq_loss", "AI-DEAL UQ objective (fused, all gradients)", nb, nv, ne, 8 * ne + 8 + 12 + 8 + 12,
         lambda: ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab))
+    flat = torch.empty((nb, H, W, 2 * ne), device=dev)
+    lib = L.load()
+    add("ig_acq_to_flat", "A_from_MEBCRN (planar -> interleaved)", nb, nv, ne, 16 * ne,
+        lambda: L.check(lib.ig_acq_to_flat(acqs.data_ptr(), nb, ne, nv, flat.data_ptr(), torch.cuda.current_stream().cuda_stream), "to_flat"))
+    back = torch.empty_like(acqs)
+    add("ig_acq_from_flat", "interleaved -> planar", nb, nv, ne, 16 * ne,
+        lambda: L.check(lib.ig_acq_from_flat(flat.data_ptr(), nb, ne, nv, back.data_ptr(), torch.cuda.current_stream().cuda_stream), "from_flat"))
+    del flat, back
     # C4: bipolar mag/phase fused objective
     mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
     mp[:, 1] -= 0.25
