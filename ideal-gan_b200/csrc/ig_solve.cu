@@ -591,7 +591,7 @@ template <int NE, int STAGES, int CH, bool UQ = false> struct TmaCfg {
 
 // Tiles are handed out dynamically (atomic counter in the scratch header) because background tiles are ~15x
 // cheaper than tissue tiles; the producer publishes the tile index of each stage next to its data.
-template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE, int NCW, bool TMAP, bool UQ>
+template <int NE, int MINB, int STAGES, bool EXACT, int CH, int MODE, int NCW, bool TMAP, bool UQ, bool OUT>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB)
 a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map_acq, const __grid_constant__ CUtensorMap map_pm) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
@@ -599,6 +599,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
     __shared__ int2 stage_tile[STAGES];             // (sample, first voxel) of the tile in each stage; sample < 0 = end
     __shared__ int chunk_ctr;                       // consumer warps draw 64-voxel chunks of the ring from here
     static_assert(!UQ || MODE == 1, "the uncertainty-aware objective lives in the register-resident path");
+    static_assert(!OUT || (MODE == 1 && !UQ), "materialised outputs: register-resident MSE path only (the UQ path writes rho itself)");
     using Cfg = TmaCfg<NE, STAGES, CH, UQ>;
     constexpr int kTileVox = Cfg::tile_vox, kPlaneBytes = Cfg::plane_bytes;
     const int nv = p.nv, ne = EXACT ? NE : p.ne;
@@ -696,6 +697,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
         constexpr int kChunks = CH;
         const float r2_sc = p.r2_sc;
         const int lane = threadIdx.x & 31;
+        [[maybe_unused]] const bool want_shat = OUT && p.shat != nullptr;       // OUT: materialise S_hat / rho_hat (MODE 1 only)
         for (;;) {
             int g = 0;
             if (lane == 0) g = atomicAdd(&chunk_ctr, 1);
@@ -736,6 +738,16 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     if (!__any_sync(0xffffffffu, active && (ar.hi0 > 0.f || ar.hi1 > 0.f))) {
                         if (active) {
                             st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, czero<pk>());
+                            if (want_shat) {
+#pragma unroll
+                                for (int e = 0; e < NE; ++e)
+                                    if (EXACT || e < ne) st_cx(p.shat + (static_cast<size_t>(b) * ne + e) * nv * 2, v0, czero<pk>());
+                            }
+                            if (OUT && !UQ && p.rho) {
+                                float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                                st_cx(rho_b, v0, czero<pk>());
+                                st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, czero<pk>());
+                            }
                             if constexpr (UQ) {
                                 // rho = 0 -> var = 0 -> the floor: every (echo, component) contributes log sqrt(1e-5), no gradient
                                 loss_part += static_cast<float>(ne) * 2.0f * -11.512925464970229f;
@@ -790,6 +802,11 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                             raw.v = e == 0 ? raw0 : sraw[e * kPlaneF4];
                             abs_range(ar, raw);
                             y[e] = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw);
+                            if (want_shat) {
+                                // Wp_e = d (c + i s) goes into this thread's own 16 bytes of the stage (the raw echo is consumed)
+                                const pk cd = vmul(m.c, m.d), sd = vmul(m.s, m.d);
+                                sraw[e * kPlaneF4] = make_float4(cd.d.x, cd.d.y, sd.d.x, sd.d.y);
+                            }
                             cmac(rw, R.pw_re, R.pw_im, y[e]);
                             cmac(rf, R.pf_re, R.pf_im, y[e]);
                             cmac(tw, R.tpw_re, R.tpw_im, y[e]);
@@ -810,6 +827,10 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                             const cx<pk> yhat = caffine(rw, R.c_re, R.c_im, rf);
                             const cx<pk> h = caffine(tw, R.c_re, R.c_im, tf);
                             const cx<pk> r{vsub(yhat.re, y[e].re), vsub(yhat.im, y[e].im)};
+                            if (want_shat && active) {
+                                const float4 wp = sraw[e * kPlaneF4];
+                                st_cx(p.shat + (static_cast<size_t>(b) * ne + e) * nv * 2, v0, cmulv(cx<pk>{mk(wp.x, wp.y), mk(wp.z, wp.w)}, yhat));
+                            }
                             cx<pk> w;
                             if constexpr (UQ) {
                                 // residual weighted by 1 / std_e; the variance terms run lane by lane (rsqrt, lg2, ex2 on the SFU)
@@ -853,6 +874,41 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                         }
                         loss_part += ls;
                         reinterpret_cast<float2 *>(p.g_pm + static_cast<size_t>(b) * nv * 2)[v0 + l] = make_float2(2.0f * p.inv_n * gphi, 2.0f * p.inv_n * gr2);
+                    }
+                }
+                if constexpr (!UQ && OUT) {
+                    if (active && (p.rho || (slow && want_shat))) {
+                        if (slow) {
+                            // ragged chunk: the materialised outputs do not depend on the mask; recompute them with the plain formulas
+                            rw = czero<pk>(); rf = czero<pk>();
+#pragma unroll
+                            for (int e = 0; e < NE; ++e) {
+                                if (EXACT || e < ne) {
+                                    const EchoRec R = T.r[e];
+                                    const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                                    const float4 q = __ldcs(reinterpret_cast<const float4 *>(p.acqs + (static_cast<size_t>(b) * ne + e) * nv * 2) + (v0 >> 1));
+                                    const cx<pk> ye = demod(m, cx<pk>{mk(q.x, q.z), mk(q.y, q.w)});
+                                    cmac(rw, R.pw_re, R.pw_im, ye);
+                                    cmac(rf, R.pf_re, R.pf_im, ye);
+                                }
+                            }
+                            if (want_shat) {
+#pragma unroll
+                                for (int e = 0; e < NE; ++e) {
+                                    if (EXACT || e < ne) {
+                                        const EchoRec R = T.r[e];
+                                        const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                                        st_cx(p.shat + (static_cast<size_t>(b) * ne + e) * nv * 2, v0, remod(m, caffine(rw, R.c_re, R.c_im, rf)));
+                                    }
+                                }
+                            }
+                        }
+                        if (p.rho) {
+                            const float inv = 1.0f / kRhoSc;
+                            float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+                            st_cx(rho_b, v0, cx<pk>{vmul(inv, rw.re), vmul(inv, rw.im)});
+                            st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<pk>{vmul(inv, rf.re), vmul(inv, rf.im)});
+                        }
                     }
                 }
                 if constexpr (UQ) {
@@ -1071,7 +1127,9 @@ static bool all_aligned(std::initializer_list<const void *> ps) {
 // Ring configuration of the fused objectives: two blocks per SM, 8 consumer warps + 1 producer warp each, 512-voxel tiles,
 // as many ring stages as fit the 227 KB of shared memory.  Measured alternatives (profiles/history_r01.md): smaller tiles, one
 // 17-warp block per SM, 10-12 consumer warps per block and batched tile claims are all slower.
-template <int NE, bool UQ> static int launch_a2a_ring(const SolveParams &p, cudaStream_t st) {
+static long ring_tiles(int nb, int nv) { return static_cast<long>(nb) * ((nv + 8 * kChunkVox - 1) / (8 * kChunkVox)); }
+
+template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const SolveParams &p, cudaStream_t st) {
     constexpr int kBudget = 216 * 1024;
     const int nb = p.nb, ne = p.ne, nv = p.nv;
     auto go = [&](auto st_c, auto minb_c, auto mode_c) {
@@ -1085,11 +1143,11 @@ template <int NE, bool UQ> static int launch_a2a_ring(const SolveParams &p, cuda
                           plane_tensor_map(&mp, p.pm, nv, nb, p.pm_bstride, C / 2, 1);
         const bool exact = exact_ok && ne == NE;
         if (tmap) {
-            if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-            return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+            if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+            return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
         }
-        if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-        return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false, UQ>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
     };
     using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
     using I3 = std::integral_constant<int, 3>;
@@ -1113,7 +1171,7 @@ template <int NE, bool UQ> static int launch_a2a_ring(const SolveParams &p, cuda
 int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
                      const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
                      float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st) {
-    if (ne > 8 || nv % 128 != 0 || pm_bstride % 4 != 0 ||
+    if (ne > 8 || nv % 128 != 0 || pm_bstride % 4 != 0 || ring_tiles(nb, nv) >= (1L << 24) ||
         !all_aligned({acqs, pm, phi_var, r2_mean, r2_var, g_pm, g_phi_var, g_r2_mean, g_r2_var, rho}))
         return IG_E_UNSUPPORTED;
     SolveParams p{};
@@ -1218,8 +1276,16 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
-        if (packed) return launch_a2a_ring<NE, false>(p, st);
+        // materialised rho_hat / S_hat ride on the ring kernel's register-resident path (NE <= 8); otherwise the plain kernel
+        if (outputs && !(packed && NE <= 8 && ring_tiles(nb, nv) < (1L << 24)))
+            return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
+        // (the ring's work counter is a float atomic, exact up to 2^24 tiles: larger batches take the plain persistent kernel)
+        if (packed && ring_tiles(nb, nv) < (1L << 24)) {
+            if constexpr (NE <= 8) {
+                if (outputs) return launch_a2a_ring<NE, false, true>(p, st);
+            }
+            return launch_a2a_ring<NE, false>(p, st);
+        }
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
 }
