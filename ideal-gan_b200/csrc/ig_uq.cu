@@ -165,6 +165,122 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
 }
 
+// =================================================================================================
+// Rician (magnitude) objective of the R2* stage, train-IDEAL-unsup.py:267-292:
+//     A2B_WF, |S_hat| = acq_to_acq(A, PM, only_mag=True);  |S_hat| <- where(A[..., :1] != 0, |S_hat|, 0)     (real channel decides, :281)
+//     var = acq_uncertainty(stop_gradient(A2B_WF), FM, R2, only_mag=True);  loss = VarMeanSquaredErrorR2()(|A|, [|S_hat|, var])
+// The upstream on |S_hat_e| = d_e |yhat_e| enters the adjoint of acq_to_acq as v_e = g_e d_e yhat_e / |yhat_e| (ig_solve.cu,
+// a2a_bwd_kernel); the per-voxel accumulators are the same.  No ragged path: the mask only gates g_e.
+// =================================================================================================
+template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a_rician_loss_kernel(const UqParams p) {
+    __shared__ SampleTab<NE> T;
+    const int nv = p.nv, ne = p.ne;
+    constexpr int L = lanes<V>::n;
+    const int tiles_ps = (nv + kThreads * L - 1) / (kThreads * L);
+    const long total = static_cast<long>(p.nb) * tiles_ps;
+    const int tile_end = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
+    const bool rem = p.r2_mean == nullptr;
+    const float fm2 = kFmSc * kFmSc, r22 = p.r2_sc * p.r2_sc;
+    int cur_b = -1;
+    float loss_part = 0.f;
+    for (int tile = static_cast<int>(total * blockIdx.x / gridDim.x); tile < tile_end; ++tile) {
+        const int b = tile / tiles_ps;
+        if (b != cur_b) {
+            if (cur_b >= 0) __syncthreads();
+            stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, ne, p.r2_sc);
+            cur_b = b;
+        }
+        const int v0 = ((tile - b * tiles_ps) * kThreads + threadIdx.x) * L;
+        if (v0 >= nv) continue;
+        const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+        const size_t plane = static_cast<size_t>(nv) * 2;
+        const V zero = splat<V>(0.f);
+        cx<V> S[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            if (e < ne) S[e] = ld_cx(p.acqs + acq_b + e * plane, v0, V{});
+        const cx<V> m0 = ld_cx(p.pm + b * p.pm_bstride, v0, V{});
+        const V phi_t = m0.re, r2 = m0.im;
+        const V pv = ld_real(p.phi_var + static_cast<size_t>(b) * nv, v0, V{});
+        V rm = zero, rv = zero;
+        if (!rem) {
+            rm = ld_real(p.r2_mean + static_cast<size_t>(b) * nv, v0, V{});
+            rv = ld_real(p.r2_var + static_cast<size_t>(b) * nv, v0, V{});
+        }
+        cx<V> rw = czero<V>(), rf = czero<V>(), tw = czero<V>(), tf = czero<V>();
+        V dec[NE], ys[NE];            // decay; observed magnitude with the mask in its sign bit (negative = masked)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const EchoRec R = T.r[e];
+                const Mod<V> m = modulator_rec<V, false>(R, phi_t, r2, zero);
+                const cx<V> y = demod(m, S[e]);
+                cmac(rw, R.pw_re, R.pw_im, y);
+                cmac(rf, R.pf_re, R.pf_im, y);
+                cmac(tw, R.tpw_re, R.tpw_im, y);
+                cmac(tf, R.tpf_re, R.tpf_im, y);
+                dec[e] = m.d;
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    const float re = lane_get(S[e].re, l), im = lane_get(S[e].im, l);
+                    lane_set(ys[e], l, copysignf(sqrtf(fmaf(re, re, im * im)), re != 0.f ? 1.0f : -1.0f));
+                }
+            }
+        }
+        UqAcc acc[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) acc[l] = UqAcc{0.f, 0.f, 0.f, 0.f};
+        cx<V> gw = czero<V>(), gf = czero<V>(), aw = czero<V>(), af = czero<V>();
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const EchoRec R = T.r[e];
+                const cx<V> yhat = caffine(rw, R.c_re, R.c_im, rf);
+                const V a2 = vfma(yhat.re, yhat.re, vmul(yhat.im, yhat.im));
+                V sc = zero;       // g_nu d / |yhat|
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    const float a2l = lane_get(a2, l), d = lane_get(dec[e], l), ysl = lane_get(ys[e], l);
+                    const float ra = a2l > 0.f ? rsqrtf(a2l) : 0.f;
+                    const float g = rician_echo(R.te, a2l, fabsf(ysl), d * a2l * ra, !signbit(ysl), lane_get(pv, l) * fm2, lane_get(rm, l) * p.r2_sc,
+                                                lane_get(rv, l) * r22, rem, acc[l]);
+                    lane_set(sc, l, g * d * ra);
+                }
+                const cx<V> v = cscale(sc, yhat);
+                gw.re = vadd(gw.re, v.re);
+                gw.im = vadd(gw.im, v.im);
+                cmac(gf, R.c_re, -R.c_im, v);
+                aw.re = vfma(R.te, v.re, aw.re);
+                aw.im = vfma(R.te, v.im, aw.im);
+                cmac(af, R.te * R.c_re, -R.te * R.c_im, v);
+            }
+        }
+        cx<V> X = cmulc(gw, tw);
+        const cx<V> x1 = cmulc(gf, tf), x2 = cmulc(aw, rw), x3 = cmulc(af, rf);
+        X.re = vsub(vadd(X.re, x1.re), vadd(x2.re, x3.re));
+        X.im = vsub(vadd(X.im, x1.im), vadd(x2.im, x3.im));
+        st_cx(p.g_pm + static_cast<size_t>(b) * nv * 2, v0, cx<V>{vmul(kTwoPi * kFmSc * p.inv_n, X.im), vmul(p.r2_sc * p.inv_n, X.re)});
+        V o_pv, o_rm, o_rv;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            loss_part += acc[l].loss;
+            lane_set(o_pv, l, acc[l].g_sphi * fm2 * p.inv_n);
+            lane_set(o_rm, l, acc[l].g_mu * p.r2_sc * p.inv_n);
+            lane_set(o_rv, l, acc[l].g_sr * r22 * p.inv_n);
+        }
+        st_real(p.g_phi_var + static_cast<size_t>(b) * nv, v0, o_pv);
+        if (p.g_r2_mean) st_real(p.g_r2_mean + static_cast<size_t>(b) * nv, v0, rem ? zero : o_rm);
+        if (p.g_r2_var) st_real(p.g_r2_var + static_cast<size_t>(b) * nv, v0, rem ? zero : o_rv);
+        if (p.rho) {
+            const float inv = 1.0f / kRhoSc;
+            float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+            st_cx(rho_b, v0, cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)});
+            st_cx(rho_b + plane, v0, cx<V>{vmul(inv, rf.re), vmul(inv, rf.im)});
+        }
+    }
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+}
+
 template <typename K> static int uq_grid(K kernel, int nb, int nv, int vpt, int *grid) {
     int dev = 0, sms = 0, occ = 0;
     IG_CUDA(cudaGetDevice(&dev));
@@ -179,6 +295,52 @@ template <typename K> static int uq_grid(K kernel, int nb, int nv, int vpt, int 
 }  // namespace ig
 
 using namespace ig;
+
+static int uq_common_checks(const char *fn, const void *acqs_d, const void *pm_d, const void *phi_var_d, const void *r2_mean_d, const void *r2_var_d,
+                            const void *tab_d, const void *g_pm_d, const void *g_phi_var_d, const void *loss_d, const void *scratch_d, int nb,
+                            int ne, int nv, size_t scratch_bytes) {
+    IG_REQUIRE(acqs_d && pm_d && phi_var_d && tab_d && g_pm_d && g_phi_var_d && loss_d && scratch_d && (!r2_mean_d == !r2_var_d), IG_E_ARG,
+               "%s: null pointer (r2_mean and r2_var go together)", fn);
+    IG_REQUIRE(nb > 0 && nv > 0 && nb <= 65535, IG_E_ARG, "%s: nb=%d (1..65535), nv=%d", fn, nb, nv);
+    IG_REQUIRE(ne >= 2 && ne <= IG_MAX_NE, IG_E_NE, "%s: ne=%d outside [2, %d]", fn, ne, IG_MAX_NE);
+    IG_REQUIRE(scratch_bytes >= ig_loss_scratch_bytes(nb, nv), IG_E_SCRATCH, "%s: scratch %zu < %zu bytes", fn, scratch_bytes,
+               ig_loss_scratch_bytes(nb, nv));
+    return 0;
+}
+
+extern "C" int ig_a2a_rician_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *phi_var_d, const float *r2_mean_d,
+                                  const float *r2_var_d, const float *tab_d, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm_d,
+                                  float *g_phi_var_d, float *g_r2_mean_d, float *g_r2_var_d, float *rho_d, float *loss_d, void *scratch_d,
+                                  size_t scratch_bytes, void *stream) {
+    if (int rc = uq_common_checks("ig_a2a_rician_loss", acqs_d, pm_d, phi_var_d, r2_mean_d, r2_var_d, tab_d, g_pm_d, g_phi_var_d, loss_d, scratch_d,
+                                  nb, ne, nv, scratch_bytes))
+        return rc;
+    UqParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d;
+    p.g_pm = g_pm_d; p.g_phi_var = g_phi_var_d; p.g_r2_mean = g_r2_mean_d; p.g_r2_var = g_r2_var_d; p.rho = rho_d; p.loss = loss_d;
+    p.scratch = scratch_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.inv_n = inv_n;
+    bool packed = nv % 2 == 0 && pm_bstride % 4 == 0;
+    for (const void *q : {static_cast<const void *>(acqs_d), static_cast<const void *>(pm_d), static_cast<const void *>(g_pm_d),
+                          static_cast<const void *>(rho_d)})
+        packed = packed && (!q || aligned16(q));
+    for (const void *q : {static_cast<const void *>(phi_var_d), static_cast<const void *>(r2_mean_d), static_cast<const void *>(r2_var_d),
+                          static_cast<const void *>(g_phi_var_d), static_cast<const void *>(g_r2_mean_d), static_cast<const void *>(g_r2_var_d)})
+        packed = packed && (!q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        int grid = 1;
+        if (packed) {
+            if (int rc = uq_grid(a2a_rician_loss_kernel<NE, pk>, nb, nv, 2, &grid)) return rc;
+            a2a_rician_loss_kernel<NE, pk><<<grid, kThreads, 0, st>>>(p);
+        } else {
+            if (int rc = uq_grid(a2a_rician_loss_kernel<NE, float>, nb, nv, 1, &grid)) return rc;
+            a2a_rician_loss_kernel<NE, float><<<grid, kThreads, 0, st>>>(p);
+        }
+        IG_CUDA(cudaGetLastError());
+        return 0;
+    });
+}
 
 extern "C" int ig_a2a_uq_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *phi_var_d, const float *r2_mean_d,
                               const float *r2_var_d, const float *tab_d, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm_d,

@@ -132,6 +132,72 @@ __device__ __forceinline__ void uq_slow_voxel(const SampleTab<NE> &T, const floa
     gr2 = r2_sc * X.re;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rician objective (VarMeanSquaredErrorR2, tf2gan/loss.py:143-162): exponentially scaled Bessel functions.
+// Chebyshev coefficients generated by tools/gen_bessel_coeffs.py (fits against scipy/mpmath, Clenshaw evaluation):
+// float32 Clenshaw evaluation: max rel err i0e 3.41e-07 on [0, 1e5], i1e 1.28e-06 on (0, 8], 1 - I1/I0 1.38e-07 on (8, 1e5]
+// ------------------------------------------------------------------------------------------------
+__device__ constexpr float kI0A[19] = {3.383976372e-01f, -3.046826723e-01f, 1.716209015e-01f, -9.490109705e-02f, 4.930528424e-02f, -2.373741481e-02f, 1.054646039e-02f, -4.324309995e-03f, 1.639475617e-03f, -5.763755745e-04f, 1.885028851e-04f, -5.754195010e-05f, 1.644844807e-05f, -4.416738358e-06f, 1.117387539e-06f, -2.670793856e-07f, 6.046995026e-08f, -1.300025026e-08f, 2.659823692e-09f};
+__device__ constexpr float kI1A[19] = {1.262935932e-01f, -1.764165184e-01f, 1.026436587e-01f, -5.294598121e-02f, 2.472644903e-02f, -1.056408489e-02f, 4.156422944e-03f, -1.513572451e-03f, 5.122859562e-04f, -1.617608158e-04f, 4.781565108e-05f, -1.327316366e-05f, 3.470251308e-06f, -8.568720265e-07f, 2.003294754e-07f, -4.445059143e-08f, 9.381537390e-09f, -1.887249834e-09f, 3.625589971e-10f};
+__device__ constexpr float kI0B[7] = {4.022452055e-01f, 3.369116478e-03f, 6.889758347e-05f, 2.891370521e-06f, 2.048918590e-07f, 2.266668991e-08f, 3.396232012e-09f};
+__device__ constexpr float kOMB[10] = {5.087044228e-01f, 9.033638646e-03f, 3.509928488e-04f, 2.400043843e-05f, 2.548542741e-06f, 3.815519410e-07f, 6.387536412e-08f, 6.605100226e-09f, -1.899860547e-09f, -1.385762091e-09f};
+
+template <int N> __device__ __forceinline__ float clenshaw(const float (&c)[N], float t) {
+    float b1 = 0.f, b2 = 0.f;
+    const float t2 = 2.0f * t;
+#pragma unroll
+    for (int k = N - 1; k >= 1; --k) {
+        const float b0 = fmaf(t2, b1, c[k] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return fmaf(t, b1, c[0] - b2);
+}
+
+// z >= 0 -> log(i0e(z)) = log I0(z) - z, and om = 1 - I1(z) / I0(z) (fitted directly above 8: it decays like 1 / (2 z))
+__device__ __forceinline__ void log_i0e_and_ratio(float z, float &log_i0e, float &om) {
+    float i0e;
+    if (z <= 8.0f) {
+        const float t = fmaf(z, 0.25f, -1.0f);
+        i0e = clenshaw(kI0A, t);
+        om = 1.0f - z * clenshaw(kI1A, t) / i0e;
+    } else {
+        const float inv = 1.0f / z, t = fmaf(16.0f, inv, -1.0f);
+        i0e = clenshaw(kI0B, t) * rsqrtf(z);
+        om = clenshaw(kOMB, t) * inv;
+    }
+    log_i0e = __logf(i0e);
+}
+
+// One (echo, voxel) term of the Rician objective and its derivatives.  y = |A_e| observed, nu = |S_hat_e| (0 where masked),
+// var = V_e |yhat_e|^2.  With s2 = max(var, 1e-5), z = y nu / s2:
+//   -loglik = -[y > 1e-5] log y + log s2 + (y - nu)^2 / (2 s2) - log i0e(z)        ((y^2 + nu^2) / (2 s2) - z, without the cancellation)
+//   d/d nu  = ((nu - y) + y om) / s2,    d/d s2 = [var >= 1e-5] (1 - ((y - nu)^2 / 2 + y nu om) / s2) / s2,    om = 1 - I1/I0 (z)
+// Returns d/d nu (0 where masked); accumulates the loss and the moment gradients like uq_echo.
+__device__ __forceinline__ float rician_echo(float te, float a2, float y, float nu_unmasked, bool keep, float s_phi, float mu, float s_r, bool rem,
+                                             UqAcc &acc) {
+    const float k = kTwoPi * te, k2 = k * k;
+    float ephi;
+    const float vphi = one_minus_exp_neg(k2 * s_phi, ephi);
+    const float er = rem ? 0.f : fast_ex2(-te * mu * kLog2e) * te * te;
+    const float var = fmaf(er, s_r, vphi) * a2;
+    const bool gate = var >= kVarFloor;
+    const float s2 = gate ? var : kVarFloor;
+    const float inv = 1.0f / s2;
+    const float nu = keep ? nu_unmasked : 0.f;
+    const float z = y * nu * inv;
+    float li0e, om;
+    log_i0e_and_ratio(z, li0e, om);
+    const float diff = y - nu;
+    acc.loss += __logf(s2) + 0.5f * diff * diff * inv - li0e - (y > 1e-5f ? __logf(y) : 0.f);
+    const float gv = gate ? inv * (1.0f - (0.5f * diff * diff + y * nu * om) * inv) : 0.f;
+    const float ga = gv * a2;
+    acc.g_sphi = fmaf(ga * k2, ephi, acc.g_sphi);
+    acc.g_mu = fmaf(-ga * te, er * s_r, acc.g_mu);
+    acc.g_sr = fmaf(ga, er, acc.g_sr);
+    return keep ? (y * om - diff) * inv : 0.f;
+}
+
 // host: the same objective on the TMA ring of ig_solve.cu (IG_E_UNSUPPORTED when the shape is not covered)
 int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
                      const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ig_a2a_bwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
     "ig_a2a_loss": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
     "ig_a2a_uq_loss": (_i, [_fp, _fp, _l, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
+    "ig_a2a_rician_loss": (_i, [_fp, _fp, _l, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
     "ig_eigenvals": (_i, [_fp, _l, _fp, _fp, _fp]),
     "ig_eigenvals_bwd": (_i, [_fp, _l, _fp, _fp, _fp, _fp]),
     "ig_cse_mag_fwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _fp, _fp]),

@@ -221,10 +221,20 @@ def _plane(t, name, nb, nv):
     return t.reshape(nb, nv)
 
 
+def a2a_rician_loss(acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc=200.0, inv_n=None, want_rho=False):
+    """Fused Rician (magnitude) objective of the R2* stage (ig_uq.cu); arguments and results as a2a_uq_loss, one loss element
+    per (echo, voxel): inv_n defaults to 1 / (nb ne H W)."""
+    return _uq_call("ig_a2a_rician_loss", acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n, want_rho, per_component=False)
+
+
 def a2a_uq_loss(acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc=200.0, inv_n=None, want_rho=False):
     """Fused uncertainty-aware objective (ig_uq.cu).  phi_var / r2_mean / r2_var: (nb,1,H,W,1) moment maps in network units
     (r2_mean = r2_var = None: rem_R2).  Returns (loss[1], g_pm (nb,1,H,W,2), g_phi_var, g_r2_mean | None, g_r2_var | None,
     rho | None), the moment gradients shaped like their inputs."""
+    return _uq_call("ig_a2a_uq_loss", acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n, want_rho, per_component=True)
+
+
+def _uq_call(symbol, acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n, want_rho, per_component):
     acqs, nb, ne, H, W = _acq_dims(acqs, False)
     pm, stride = _pm_view(pm, nb, H, W, False)
     if (r2_mean is None) != (r2_var is None):
@@ -233,7 +243,7 @@ def a2a_uq_loss(acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc=200.0, inv_n=None
     pv = _plane(phi_var, "phi_var", nb, nv)
     rm = None if r2_mean is None else _plane(r2_mean, "r2_mean", nb, nv)
     rv = None if r2_var is None else _plane(r2_var, "r2_var", nb, nv)
-    inv_n = 1.0 / acqs.numel() if inv_n is None else inv_n
+    inv_n = (1.0 / acqs.numel() if per_component else 2.0 / acqs.numel()) if inv_n is None else inv_n
     dev = acqs.device
     g_pm = torch.empty((nb, 1, H, W, 2), dtype=torch.float32, device=dev)
     g_pv = torch.empty(phi_var.shape, dtype=torch.float32, device=dev)
@@ -242,9 +252,9 @@ def a2a_uq_loss(acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc=200.0, inv_n=None
     rho = torch.empty((nb, 2, H, W, 2), dtype=torch.float32, device=dev) if want_rho else None
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     scr = loss_scratch(dev, nb, nv)
-    L.check(L.load().ig_a2a_uq_loss(acqs.data_ptr(), pm.data_ptr(), stride, pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv,
-                                    float(r2_sc), float(inv_n), g_pm.data_ptr(), g_pv.data_ptr(), _ptr(g_rm), _ptr(g_rv), _ptr(rho),
-                                    loss.data_ptr(), scr.data_ptr(), scr.numel(), _stream()), "ig_a2a_uq_loss")
+    L.check(getattr(L.load(), symbol)(acqs.data_ptr(), pm.data_ptr(), stride, pv.data_ptr(), _ptr(rm), _ptr(rv), tab.data_ptr(), nb, ne, nv,
+                                      float(r2_sc), float(inv_n), g_pm.data_ptr(), g_pv.data_ptr(), _ptr(g_rm), _ptr(g_rv), _ptr(rho),
+                                      loss.data_ptr(), scr.data_ptr(), scr.numel(), _stream()), symbol)
     return loss, g_pm, g_pv, g_rm, g_rv, rho
 
 

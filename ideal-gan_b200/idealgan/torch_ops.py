@@ -141,10 +141,11 @@ class _A2AUqLoss(torch.autograd.Function):
     """Fused uncertainty-aware objective: forward produces every gradient, backward scales them."""
 
     @staticmethod
-    def forward(ctx, acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n):
-        loss, g_pm, g_pv, g_rm, g_rv, rho = ops.a2a_uq_loss(acqs.contiguous(), pm.contiguous(), phi_var.contiguous(),
-                                                            None if r2_mean is None else r2_mean.contiguous(),
-                                                            None if r2_var is None else r2_var.contiguous(), tab, r2_sc, inv_n, want_rho=True)
+    def forward(ctx, acqs, pm, phi_var, r2_mean, r2_var, tab, r2_sc, inv_n, rician=False):
+        fused = ops.a2a_rician_loss if rician else ops.a2a_uq_loss
+        loss, g_pm, g_pv, g_rm, g_rv, rho = fused(acqs.contiguous(), pm.contiguous(), phi_var.contiguous(),
+                                                  None if r2_mean is None else r2_mean.contiguous(),
+                                                  None if r2_var is None else r2_var.contiguous(), tab, r2_sc, inv_n, want_rho=True)
         if pm.shape[1] != 1:
             full = torch.zeros_like(pm)
             full[:, :1] = g_pm
@@ -158,7 +159,19 @@ class _A2AUqLoss(torch.autograd.Function):
     def backward(ctx, g, _g_rho):
         saved = ctx.saved_tensors
         g_rm, g_rv = (saved[2] * g, saved[3] * g) if ctx.has_r2 else (None, None)
-        return None, saved[0] * g, saved[1] * g, g_rm, g_rv, None, None, None
+        return None, saved[0] * g, saved[1] * g, g_rm, g_rv, None, None, None, None
+
+
+def physics_loss_a2a_rician(acqs, pm, phi_var, r2_mean, r2_var, te, field=1.5, r2_sc=200.0, inv_n=None):
+    """The R2* stage objective of AI-DEAL as one kernel (train-IDEAL-unsup.py:267-292): acq_to_acq(only_mag=True) -> mask on the
+    real channel -> acq_uncertainty(only_mag=True) on the stop-gradient estimate -> VarMeanSquaredErrorR2 (Rician negative
+    log-likelihood) against |A|.  Same arguments and results as physics_loss_a2a_uq; inv_n: 1 / (nb ne H W of the global batch)."""
+    tab, ne = _tables(te, field, acqs.device)
+    _check_batch(tab.shape[0], acqs.shape[0])
+    if ne != acqs.shape[1]:
+        raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[1]}")
+    inv_n = 2.0 / acqs.numel() if inv_n is None else float(inv_n)
+    return _A2AUqLoss.apply(acqs, pm, phi_var, r2_mean, r2_var, tab, float(r2_sc), inv_n, True)
 
 
 def physics_loss_a2a_uq(acqs, pm, phi_var, r2_mean, r2_var, te, field=1.5, r2_sc=200.0, inv_n=None):

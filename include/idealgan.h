@@ -137,6 +137,14 @@ int ig_a2a_uq_loss(const float *acqs_d, const float *pm_d, long pm_bstride, cons
                    float *g_phi_var_d, float *g_r2_mean_d, float *g_r2_var_d, float *rho_d, float *loss_d, void *scratch_d,
                    size_t scratch_bytes, void *stream);
 
+/* Rician (magnitude) objective of the R2* stage (train-IDEAL-unsup.py:267-292; tf2gan/loss.py:143-162): same arguments and outputs;
+ * loss_d[0] = inv_n * sum over echoes of -loglik(|A_e| ; nu = where(Re A_e != 0, |S_hat_e|, 0), sigma^2 = max(var_e, 1e-5)),
+ * var_e from acq_uncertainty(only_mag=True).  inv_n = 1 / (nb ne nv) of the GLOBAL batch (one element per echo and voxel). */
+int ig_a2a_rician_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *phi_var_d, const float *r2_mean_d,
+                       const float *r2_var_d, const float *tab_d, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm_d,
+                       float *g_phi_var_d, float *g_r2_mean_d, float *g_r2_var_d, float *rho_d, float *loss_d, void *scratch_d,
+                       size_t scratch_bytes, void *stream);
+
 /* ---- second tier: magnitude fit, uncertainty propagation, PDFF (IDEAL_model.py:100-138,314-401,628-767) ---- */
 /* eigenvals: x_d (n, 3) = (a, b, c) -> xy_d (n, 2), ratio_d (n); adjoint with optional upstreams */
 int ig_eigenvals(const float *x_d, long n, float *xy_d, float *ratio_d, void *stream);

@@ -366,6 +366,42 @@ def gen_uq():
     save("uq", **out)
 
 
+def gen_rician():
+    """The R2* stage objective of train-IDEAL-unsup.py:267-292 from the reference's own functions.  The library's acq_to_acq
+    has no only_mag argument: its callers' |S_hat| is formed here as they form |A| (:269), sqrt(sum(square))."""
+    rng = np.random.default_rng(6)
+    out = {}
+    for name, nb, ne, field, rem in [("ric_orig6", 2, 6, 1.5, False), ("ric_rand5_rem", 2, 5, 1.5, True)]:
+        maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0, masked=False)          # no background: sqrt'(0) is NaN in autodiff
+        te = synth.te_orig(nb, ne) if name == "ric_orig6" else synth.te_random(nb, ne, rng)
+        with torch.no_grad():
+            acqs = synth.add_noise(N(wf.IDEAL_Layer(field=field)(T(maps), te=T(te))), rng)
+        acqs[0, 1, 2:4, 3, 0] = 0.0                                                   # real channel zero: masked elements
+        pm = (maps[:, 2:3] + 0.03 * rng.standard_normal(maps[:, 2:3].shape).astype(np.float32)).astype(np.float32)
+        phi_v = rng.uniform(1e-5, 4e-3, size=(nb, 1, H, W, 1)).astype(np.float32)
+        r2_m = np.ascontiguousarray(pm[:, :, :, :, 1:2])
+        r2_v = rng.uniform(1e-5, 3e-3, size=(nb, 1, H, W, 1)).astype(np.float32)
+        phi_v[1, 0, :3] = 0.0                                                          # variance floor
+        r2_v[1, 0, :3] = 0.0
+        a = T(acqs)
+        p, pv, rm, rv = T(pm, grad=True), T(phi_v, grad=True), T(r2_m, grad=True), T(r2_v, grad=True)
+        rho = wf.get_rho(a, p, field=field, te=T(te))
+        recon = wf.acq_to_acq(a, p, te=T(te), field=field)
+        mag = tf_shim.math.sqrt(tf_shim.reduce_sum(tf_shim.square(recon), axis=-1, keepdims=True))
+        mag_m = torch.where(a[..., :1] != 0.0, mag, torch.zeros_like(mag))
+        var = wf.acq_uncertainty(rho.detach(), Moments(None, pv), Moments(rm, rv), ne=ne, te=T(te), field=field, rem_R2=rem, only_mag=True)
+        y = tf_shim.math.sqrt(tf_shim.reduce_sum(tf_shim.square(a), axis=-1, keepdims=True))
+        loss = ref_loss.VarMeanSquaredErrorR2()(y, tf_shim.concat([mag_m, var], axis=-1))
+        grads = torch.autograd.grad(loss, [p, pv, rm, rv], allow_unused=True)
+        g = [N(x) if x is not None else np.zeros(tuple(t.shape), np.float32) for x, t in zip(grads, [p, pv, rm, rv])]
+        assert all(np.isfinite(x).all() for x in g)
+        out.update({f"{name}_acqs": acqs, f"{name}_te": te, f"{name}_field": np.float32(field), f"{name}_rem": np.bool_(rem),
+                    f"{name}_pm": pm, f"{name}_phi_v": phi_v, f"{name}_r2_m": r2_m, f"{name}_r2_v": r2_v,
+                    f"{name}_loss": np.float32(loss.item()), f"{name}_var": N(var), f"{name}_mag": N(mag),
+                    f"{name}_gpm": g[0], f"{name}_gphi_v": g[1], f"{name}_gr2_m": g[2], f"{name}_gr2_v": g[3]})
+    save("rician", **out)
+
+
 def _reference_data_functions(names):
     """data.py cannot be imported here (h5py, pydicom, nibabel, skimage are absent), so the SOURCE of the named top-level
     functions is cut out of /root/reference/data.py with `ast` and executed unmodified against the shim."""
@@ -411,4 +447,5 @@ if __name__ == "__main__":
     gen_losses()
     gen_tier2()
     gen_uq()
+    gen_rician()
     gen_layout()

@@ -525,6 +525,22 @@ def physics_loss_a2a_uq(acqs, param_maps, phi_var, r2_mean=None, r2_var=None, te
     return var_mse(acqs, torch.cat([masked, var], dim=-1)), rho, recon, var
 
 
+def physics_loss_a2a_rician(acqs, param_maps, phi_var, r2_mean=None, r2_var=None, te=None, field=1.5, r2_sc=200.0,
+                            rdtype=torch.float32):
+    """The R2* stage of AI-DEAL (train-IDEAL-unsup.py:267-292): magnitudes of the resynthesised echoes, masked where the REAL
+    channel of A is zero (:281), magnitude variance from acq_uncertainty(only_mag=True) on the stop-gradient estimate,
+    Rician negative log-likelihood VarMeanSquaredErrorR2 (tf2gan/loss.py:143-162) against |A|.
+    Returns (loss, rho_hat/rho_sc, |S_hat| unmasked, var)."""
+    acqs = _t(acqs, rdtype)
+    rho, mag = acq_to_acq(acqs, param_maps, te=te, field=field, r2_sc=r2_sc, only_mag=True, rdtype=rdtype)
+    masked = torch.where(acqs[..., :1] != 0, mag, torch.zeros_like(mag))
+    rem = r2_mean is None
+    var = acq_uncertainty(rho.detach(), Moments(None, phi_var), None if rem else Moments(r2_mean, r2_var), ne=acqs.shape[1], te=te,
+                          r2_sc=r2_sc, field=field, rem_R2=rem, only_mag=True, rdtype=rdtype)
+    y = torch.sqrt(torch.sum(acqs * acqs, dim=-1, keepdim=True))
+    return var_mse_r2(y, torch.cat([masked, var], dim=-1)), rho, mag, var
+
+
 def physics_loss_fwd(acqs, out_maps, te, field=1.5, r2_sc=200.0, model="wfpm", rdtype=torch.float32):
     """Forward-model -> mask -> MSE objective (train-IDEAL-single.py:154-157 for model='magpha')."""
     fn = {"wfpm": IDEAL_model, "ffpd": IDEAL_mag, "magpha": IDEAL_mag_phase}[model]

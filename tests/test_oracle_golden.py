@@ -251,6 +251,28 @@ def test_uq_objective(golden, name, rdtype, tol):
         assert not g[name + "_gr2_m"].any() and not g[name + "_gr2_v"].any()
 
 
+@pytest.mark.parametrize("name", ["ric_orig6", "ric_rand5_rem"])
+def test_rician_objective(golden, name):
+    """train-IDEAL-unsup.py:267-292 composed from the reference's functions (oracle/gen_golden.py:gen_rician).  The moment gradients
+    carry 1/sigma^4 of fp32 variances: the reference's own fp32 and fp64 evaluations differ by up to 4e-4 there."""
+    g = golden("rician")
+    rem = bool(g[name + "_rem"])
+    for rdtype, tol_pm, tol_mom in [(torch.float32, 5e-6, 3e-4), (torch.float64, 1e-5, 1e-3)]:
+        p, pv = tt(g[name + "_pm"], True, rdtype), tt(g[name + "_phi_v"], True, rdtype)
+        rm, rv = tt(g[name + "_r2_m"], True, rdtype), tt(g[name + "_r2_v"], True, rdtype)
+        loss, _, mag, var = orc.physics_loss_a2a_rician(tt(g[name + "_acqs"]), p, pv, None if rem else rm, None if rem else rv,
+                                                        te=tt(g[name + "_te"]), field=float(g[name + "_field"]), rdtype=rdtype)
+        assert abs(loss.item() - float(g[name + "_loss"])) <= 1e-5 * abs(float(g[name + "_loss"]))
+        assert_close(npy(mag), g[name + "_mag"], 1e-5, "|S_hat|")
+        assert_close(npy(var), g[name + "_var"], 2e-5, "var")
+        grads = torch.autograd.grad(loss, [p, pv] + ([] if rem else [rm, rv]))
+        assert_close(npy(grads[0]), g[name + "_gpm"], tol_pm, "grad pm")
+        assert_close(npy(grads[1]), g[name + "_gphi_v"], tol_mom, "grad phi var")
+        if not rem:
+            assert_close(npy(grads[2]), g[name + "_gr2_m"], tol_mom, "grad r2 mean")
+            assert_close(npy(grads[3]), g[name + "_gr2_v"], tol_mom, "grad r2 var")
+
+
 def test_layout_adapters(golden):
     """data.py:262-329 (oracle/gen_golden.py:gen_layout runs the reference's own function source): pure data movement."""
     g = golden("layout")

@@ -301,6 +301,55 @@ def test_uq_objective_vs_fp64_oracle(hw, ne):
         assert_close(host(got), host(want.float()), 2e-5, "grad " + what)
 
 
+@pytest.mark.parametrize("name", ["ric_orig6", "ric_rand5_rem"])
+def test_rician_objective_vs_reference_vectors(golden, name):
+    """Fused Rician objective against the composition of the reference's own functions.  Moment gradients: see
+    tests/test_oracle_golden.py::test_rician_objective for the reference's own fp32 noise (up to 4e-4)."""
+    g = golden("rician")
+    rem = bool(g[name + "_rem"])
+    tab = ops.gen_tables(dev(g[name + "_te"]), float(g[name + "_field"]))
+    loss, g_pm, g_pv, g_rm, g_rv, _ = ops.a2a_rician_loss(dev(g[name + "_acqs"]), dev(g[name + "_pm"]), dev(g[name + "_phi_v"]),
+                                                          None if rem else dev(g[name + "_r2_m"]), None if rem else dev(g[name + "_r2_v"]), tab)
+    ref = float(g[name + "_loss"])
+    assert abs(loss.item() - ref) <= TOL * abs(ref), (loss.item(), ref)
+    assert_close(host(g_pm), g[name + "_gpm"], TOL, "grad pm")
+    assert_close(host(g_pv), g[name + "_gphi_v"], 1e-3, "grad phi var")
+    if not rem:
+        assert_close(host(g_rm), g[name + "_gr2_m"], 1e-3, "grad r2 mean")
+        assert_close(host(g_rv), g[name + "_gr2_v"], 1e-3, "grad r2 var")
+
+
+@pytest.mark.parametrize("hw", [(9, 7), (48, 64)])
+@pytest.mark.parametrize("ne", [3, 6, 12])
+def test_rician_objective_vs_fp64_oracle(hw, ne):
+    """Against the fp64 restatement: disc-masked data (background: |S_hat| = 0, where autodiff has NaN the kernel has 0),
+    masked real channels, floored variances, scalar and packed kernels."""
+    rng = np.random.default_rng(99 + ne)
+    H, W = hw
+    nb = 2
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+    te = synth.te_random(nb, ne, rng, d_te_min=0.9e-3 if ne > 8 else 1.6e-3, d_te_d=0.3e-3 if ne > 8 else 1.0e-3)
+    acqs = synth.add_noise(host(orc.IDEAL_model(cpu(maps), [1.5, cpu(te)])), rng)
+    acqs[0, 0, H // 2, W // 2, 0] = 0.0
+    acqs[1, ne - 1, H // 2, 1:4, 0] = 0.0
+    pm = (maps[:, 2:3] + 0.03 * rng.standard_normal(maps[:, 2:3].shape).astype(np.float32) * (maps[:, 2:3] != 0)).astype(np.float32)
+    tissue = (maps[:, 0:1, :, :, 0:1] != 0).astype(np.float32)
+    phi_v = rng.uniform(1e-5, 4e-3, size=(nb, 1, H, W, 1)).astype(np.float32) * tissue
+    r2_m = np.ascontiguousarray(pm[..., 1:2])
+    r2_v = rng.uniform(1e-5, 3e-3, size=(nb, 1, H, W, 1)).astype(np.float32) * tissue
+    dt = torch.float64
+    p, pv, rm, rv = (cpu(x).to(dt).requires_grad_(True) for x in (pm, phi_v, r2_m, r2_v))
+    lref, rho_r, _, _ = orc.physics_loss_a2a_rician(cpu(acqs), p, pv, rm, rv, te=cpu(te), rdtype=dt)
+    gref = [torch.nan_to_num(x, nan=0.0) for x in torch.autograd.grad(lref, [p, pv, rm, rv])]
+    tab = ops.gen_tables(dev(te), 1.5)
+    loss, g_pm, g_pv, g_rm, g_rv, rho = ops.a2a_rician_loss(dev(acqs), dev(pm), dev(phi_v), dev(r2_m), dev(r2_v), tab, want_rho=True)
+    assert abs(loss.item() - lref.item()) <= TOL * abs(lref.item())
+    assert_close(host(rho), host(rho_r.float()), TOL, "rho")
+    for got, want, what, tol in zip((g_pm, g_pv, g_rm, g_rv), gref, ("pm", "phi var", "r2 mean", "r2 var"), (2e-5, 5e-5, 5e-5, 5e-5)):
+        assert np.isfinite(host(got)).all()
+        assert_close(host(got), host(want.float()), tol, "grad " + what)
+
+
 def test_layout_adapters_vs_reference_vectors(golden):
     """data.A_from_MEBCRN / B_from_MEBCRN / B_to_MEBCRN: bit-exact data movement (the mag/phase branch: 1e-6, it has a sincos)."""
     from idealgan import layout

@@ -95,6 +95,8 @@ def main():
     rm = pm[..., 1:2].contiguous()
     add("ig_a2a_uq_loss", "AI-DEAL UQ objective (fused, all gradients)", nb, nv, ne, 8 * ne + 8 + 12 + 8 + 12,
         lambda: ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab))
+    add("ig_a2a_rician_loss", "AI-DEAL R2* stage objective (Rician, fused)", nb, nv, ne, 8 * ne + 8 + 12 + 8 + 12,
+        lambda: ops.a2a_rician_loss(acqs, pm, pv, rm, rv, tab))
     flat = torch.empty((nb, H, W, 2 * ne), device=dev)
     lib = L.load()
     add("ig_acq_to_flat", "A_from_MEBCRN (planar -> interleaved)", nb, nv, ne, 16 * ne,
