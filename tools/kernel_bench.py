@@ -97,6 +97,17 @@ def main():
         lambda: ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab))
     add("ig_a2a_rician_loss", "AI-DEAL R2* stage objective (Rician, fused)", nb, nv, ne, 8 * ne + 8 + 12 + 8 + 12,
         lambda: ops.a2a_rician_loss(acqs, pm, pv, rm, rv, tab))
+    # second tier: magnitude fit, uncertainty propagation
+    mag = torch.sqrt((acqs ** 2).sum(-1, keepdim=True)).contiguous()
+    r2map = pm[..., 1:2].contiguous().reshape(nb, 1, H, W, 1)
+    add("ig_cse_mag_fwd", "CSE_mag (rho, fit, demod, ls, unc)", nb, nv, ne, 12 * ne + 28,
+        lambda: ops.cse_mag_fwd(mag, r2map, tab))
+    rho_hat, _ = ops.a2a_fwd(acqs, pm, tab)
+    add("ig_acq_unc_fwd", "acq_uncertainty", nb, nv, ne, 16 + 12 + 8 * ne, lambda: ops.acq_unc_fwd(rho_hat, pv, rm, rv, tab, ne))
+    add("ig_pdff_unc", "PDFF_uncertainty (weighted LS per voxel)", nb, nv, ne, 8 * ne + 16 + 16 + 16,
+        lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab))
+    add("ig_pdff_extract", "PDFF map", nb, nv, ne, 16 + 4, lambda: ops.pdff_extract(rho_hat))
+    del mag, rho_hat
     flat = torch.empty((nb, H, W, 2 * ne), device=dev)
     lib = L.load()
     add("ig_acq_to_flat", "A_from_MEBCRN (planar -> interleaved)", nb, nv, ne, 16 * ne,
