@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
 // work items and taking part in the loss reduction ONCE at the end -- with one block per tile the 18 k ticket atomics
 // of a 64-slice batch all hit one address and every block sits out its own L2 round trip before it can retire.
 template <int NE, typename V, int MODEL>
-__global__ void __launch_bounds__(kThreads) ideal_loss_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kThreads, MODEL == IG_MODEL_MAGPHA ? 2 : 3) ideal_loss_kernel(const FwdParams p) {   // measured: 80 registers pay off except for mag/phase (spills)
     __shared__ SampleTab<NE> T;
     const int tiles_ps = (p.nv + kThreads * lanes<V>::n - 1) / (kThreads * lanes<V>::n);
     const long total = static_cast<long>(p.nb) * tiles_ps;

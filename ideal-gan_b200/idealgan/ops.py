@@ -150,7 +150,6 @@ def get_rho_bwd(acqs, pm, tab, g_rho, g_demod, r2_sc=200.0, flags=0, need_acqs=T
     pm, stride = _pm_view(pm, nb, H, W, flat)
     g_rho = None if g_rho is None else _chk(g_rho, "grad rho")
     g_demod = None if g_demod is None else _chk(g_demod, "grad demod")
-    g_pm = torch.zeros_like(pm)
     bip_ptr = bip_stride = 0
     g_bip = None
     row = torch.empty((nb, H, W, 2), dtype=torch.float32, device=acqs.device)
@@ -163,7 +162,10 @@ def get_rho_bwd(acqs, pm, tab, g_rho, g_demod, r2_sc=200.0, flags=0, need_acqs=T
                                     _stream()), "ig_get_rho_bwd")
     if flat:
         g_pm = row
+    elif pm.shape[1] == 1:
+        g_pm = row.unsqueeze(1)                 # the kernel's dense row IS the (nb, 1, H, W, 2) gradient: no fill, no copy
     else:
+        g_pm = torch.zeros_like(pm)
         g_pm[:, 0] = row
         if g_bip is not None:
             g_pm[:, -1] = g_bip
