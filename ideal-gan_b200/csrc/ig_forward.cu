@@ -8,6 +8,8 @@
 //     S_e = exp(-te_e R) exp(i (2 pi te_e phi + s_e beta)) (rho_W + c_e rho_F),   s_e = (-1)^e
 // Algorithmic HBM bytes per voxel (ne = 6): forward 24|32 read + 48 written; backward 48 + 24|32 read
 // + 24|32 written; fused loss 48 + 24|32 read + 24|32 written.
+#include <stdlib.h>
+
 #include "ig_common.cuh"
 
 namespace ig {
@@ -245,6 +247,46 @@ __global__ void __launch_bounds__(kThreads, MODEL == IG_MODEL_MAGPHA ? 2 : 3) id
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
 }
 
+// Alternative split of the same objective: one block per tile (the shape that streams at the roofline for the adjoint), each
+// block leaving its partial with a plain store, and a one-block kernel adding the partials in index order in fp64.  No atomics,
+// no fences, bit-reproducible.
+template <int NE, typename V, int MODEL>
+__global__ void __launch_bounds__(kThreads) ideal_loss_grid_kernel(const FwdParams p) {
+    __shared__ SampleTab<NE> T;
+    __shared__ float warp_part[kThreads / 32];
+    const int b = blockIdx.y;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
+    float v = v0 < p.nv ? ideal_voxels<NE, V, MODEL, MODE_LOSS>(p, T, b, v0) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) s += warp_part[w];
+        reinterpret_cast<float *>(reinterpret_cast<char *>(p.scratch) + kScratchHeader)[blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024) loss_finish_kernel(const void *scratch, int n, float scale, float *loss_out) {
+    __shared__ double part[32];
+    grid_dependency_wait();
+    const float *partials = reinterpret_cast<const float *>(reinterpret_cast<const char *>(scratch) + kScratchHeader);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += static_cast<double>(partials[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 32; ++w) s += part[w];
+        loss_out[0] = static_cast<float>(s * static_cast<double>(scale));
+    }
+}
+
 template <typename K> static int resident_grid(K kernel, int nb, int nv, int vpt, int *grid) {
     int dev = 0, sms = 0, occ = 0;
     IG_CUDA(cudaGetDevice(&dev));
@@ -266,6 +308,17 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
     return dispatch_ne(p.ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         if constexpr (MODE == MODE_LOSS) {
+            // measured at 64 x 384 x 384 x 6: the grid + finish pair wins for the complex-row models (0.159 vs 0.165 ms), the
+            // persistent kernel for mag/phase, whose 128 registers leave too few warps for the one-tile-per-block shape (0.213 vs 0.251 ms)
+            if (MODEL != IG_MODEL_MAGPHA) {
+                const dim3 g = grid_for(p.nb, p.nv, packed ? 2 : 1);
+                if (packed) ideal_loss_grid_kernel<NE, pk, MODEL><<<g, kThreads, 0, st>>>(p);
+                else ideal_loss_grid_kernel<NE, float, MODEL><<<g, kThreads, 0, st>>>(p);
+                IG_CUDA(cudaGetLastError());
+                loss_finish_kernel<<<1, 1024, 0, st>>>(p.scratch, static_cast<int>(g.x * g.y), p.inv_n, p.loss);
+                IG_CUDA(cudaGetLastError());
+                return 0;
+            }
             int grid = 1;
             if (packed) {
                 if (int rc = resident_grid(ideal_loss_kernel<NE, pk, MODEL>, p.nb, p.nv, 2, &grid)) return rc;
