@@ -567,7 +567,13 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
 }
 
 // =================================================================================================
-// TMA-pipelined variant of the fused objective (packed path, no materialised outputs): the headline kernel.
+// TMA-pipelined ring kernel of the fused objectives (packed path): the headline kernel and its two siblings.
+//   UQ  = false, OUT = false : config-2 objective, loss + d/dPM only (64 B/voxel)            -- bench.py's kernel
+//   UQ  = false, OUT = true  : the same with rho_hat / S_hat materialised (128 B/voxel)
+//   UQ  = true               : the uncertainty-aware objective of ig_uq.cu (88 B/voxel)
+// Template parameters: NE echo bucket, MINB blocks per SM, STAGES ring depth, EXACT (ne == NE: no per-echo predicates),
+// CH chunks (of 64 voxels) per tile, MODE 1 = y in registers / 0 = y parked in the stage, NCW consumer warps,
+// TMAP = tensor-map loads / bulk copies.
 //
 // Warp-specialised persistent blocks: NCW consumer warps + 1 producer warp.  The producer's lane 0 claims tiles
 // from a global counter and streams each one (ne echo planes + the PM row + the sample's echo records) into a
