@@ -157,7 +157,7 @@ __device__ __forceinline__ void write_grads(float *g_b, int rows_or_ch, int nv, 
 
 // one thread's voxels of sample b starting at v0: decode, all echoes, write-out; returns the thread's loss partial
 template <int NE, typename V, int MODEL, int MODE>
-__device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTab<NE> &T, int b, int v0) {
+__device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTab<NE> &T, int b, int v0, float2 *stile = nullptr, int spitch = 0) {
     const int nv = p.nv, ne = p.ne;
     const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * p.rows_or_ch
                                                         : static_cast<size_t>(p.rows_or_ch) * nv * 2;
@@ -184,7 +184,14 @@ __device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTa
             const cx<V> yhat = caffine(x.rhoW, T.r[e].c_re, T.r[e].c_im, x.rhoF);
             const cx<V> shat = cmulv(w, yhat);
             if constexpr (MODE == MODE_FWD) {
-                st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                if (stile) {
+                    // channel-interleaved output: staged as [voxel][echo] in shared memory, written out linearly by the block
+#pragma unroll
+                    for (int l = 0; l < lanes<V>::n; ++l)
+                        stile[(threadIdx.x * lanes<V>::n + l) * spitch + e] = make_float2(lane_get(shat.re, l), lane_get(shat.im, l));
+                } else {
+                    st_cx(p.out + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                }
             } else {
                 cx<V> G;
                 if constexpr (MODE == MODE_BWD) {
@@ -221,6 +228,29 @@ __global__ void __launch_bounds__(kThreads) ideal_kernel(const FwdParams p) {
     stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, p.r2_sc);
     const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
     if (v0 < p.nv) ideal_voxels<NE, V, MODEL, MODE>(p, T, b, v0);
+}
+
+// Forward model with the channel-interleaved output (nb, nv, 2 ne) of data.A_from_MEBCRN (train-sup.py:242-244 runs IDEAL_op and
+// then that adapter): the block's tile is transposed through shared memory ([voxel][echo], odd pitch) and leaves as one
+// contiguous, fully coalesced run of float2 -- a strided store straight from the registers measured 3 x slower than the
+// planar kernel, slower even than planar kernel + adapter.
+template <int NE, typename V, int MODEL>
+__global__ void __launch_bounds__(kThreads) ideal_fwd_flat_kernel(const FwdParams p) {
+    __shared__ SampleTab<NE> T;
+    extern __shared__ float2 flat_tile[];
+    const int b = blockIdx.y, ne = p.ne, pitch = ne | 1;
+    constexpr int kTile = kThreads * lanes<V>::n;
+    stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, ne, p.r2_sc);
+    const int t0 = blockIdx.x * kTile;
+    const int v0 = t0 + threadIdx.x * lanes<V>::n;
+    if (v0 < p.nv) ideal_voxels<NE, V, MODEL, MODE_FWD>(p, T, b, v0, flat_tile, pitch);
+    __syncthreads();
+    const int nvox = min(kTile, p.nv - t0);
+    float2 *dst = reinterpret_cast<float2 *>(p.out) + (static_cast<size_t>(b) * p.nv + t0) * ne;
+    for (int i = threadIdx.x; i < nvox * ne; i += kThreads) {
+        const int v = i / ne, e = i - v * ne;
+        __stcs(dst + i, flat_tile[v * pitch + e]);
+    }
 }
 
 // Fused objective: a persistent grid (one resident wave), each block walking a contiguous range of (sample, tile)
@@ -327,6 +357,16 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
                 if (int rc = resident_grid(ideal_loss_kernel<NE, float, MODEL>, p.nb, p.nv, 1, &grid)) return rc;
                 ideal_loss_kernel<NE, float, MODEL><<<grid, kThreads, 0, st>>>(p);
             }
+        } else if (MODE == MODE_FWD && (p.flags & IG_F_FLAT)) {
+            if constexpr (MODE == MODE_FWD) {
+                const size_t smem = static_cast<size_t>(kThreads) * (packed ? 2 : 1) * (p.ne | 1) * sizeof(float2);
+                if (packed) {
+                    IG_CUDA(cudaFuncSetAttribute(ideal_fwd_flat_kernel<NE, pk, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    ideal_fwd_flat_kernel<NE, pk, MODEL><<<grid_for(p.nb, p.nv, 2), kThreads, smem, st>>>(p);
+                } else {
+                    ideal_fwd_flat_kernel<NE, float, MODEL><<<grid_for(p.nb, p.nv, 1), kThreads, smem, st>>>(p);
+                }
+            }
         } else if (packed) {
             ideal_kernel<NE, pk, MODEL, MODE><<<grid_for(p.nb, p.nv, 2), kThreads, 0, st>>>(p);
         } else {
@@ -373,6 +413,7 @@ extern "C" int ig_ideal_bwd(int model, const float *maps_d, int rows_or_ch, cons
                             int flags, const float *gout_d, float *gmaps_d, void *stream) {
     IG_REQUIRE(maps_d && tab_d && gout_d && gmaps_d, IG_E_ARG, "ig_ideal_bwd: null pointer");
     if (int rc = check_model_args("ig_ideal_bwd", model, rows_or_ch, nb, ne, nv)) return rc;
+    IG_REQUIRE(!(flags & IG_F_FLAT), IG_E_UNSUPPORTED, "ig_ideal_bwd: the interleaved layout is a forward-only output option");
     FwdParams p{};
     p.maps = maps_d; p.tab = tab_d; p.gout = gout_d; p.gmaps = gmaps_d; p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv;
     p.flags = flags; p.r2_sc = r2_sc;
@@ -384,6 +425,7 @@ extern "C" int ig_ideal_loss(int model, const float *maps_d, int rows_or_ch, con
                              size_t scratch_bytes, void *stream) {
     IG_REQUIRE(maps_d && tab_d && acqs_d && gmaps_d && loss_d && scratch_d, IG_E_ARG, "ig_ideal_loss: null pointer");
     if (int rc = check_model_args("ig_ideal_loss", model, rows_or_ch, nb, ne, nv)) return rc;
+    IG_REQUIRE(!(flags & IG_F_FLAT), IG_E_UNSUPPORTED, "ig_ideal_loss: the interleaved layout is a forward-only output option");
     IG_REQUIRE(scratch_bytes >= ig_loss_scratch_bytes(nb, nv), IG_E_SCRATCH, "ig_ideal_loss: scratch %zu < %zu bytes", scratch_bytes,
                ig_loss_scratch_bytes(nb, nv));
     FwdParams p{};

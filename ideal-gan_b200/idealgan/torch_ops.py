@@ -37,11 +37,16 @@ class _IdealForward(torch.autograd.Function):
     def backward(ctx, gout):
         maps, tab = ctx.saved_tensors
         model, ne, r2_sc, flags = ctx.cfg
-        return ops.ideal_bwd(model, maps, tab, ne, gout.contiguous(), r2_sc, flags), None, None, None, None, None
+        gout = gout.contiguous()
+        if flags & L.F_FLAT:                     # interleaved upstream -> planar (the adapter's adjoint), then the usual adjoint kernel
+            from . import layout
+            gout, flags = layout._acq_from_flat(gout), flags & ~L.F_FLAT
+        return ops.ideal_bwd(model, maps, tab, ne, gout, r2_sc, flags), None, None, None, None, None
 
 
 def ideal_forward(model, maps, te, field=1.5, r2_sc=200.0, flags=0):
-    """Forward signal model (IDEAL_model / IDEAL_mag / IDEAL_mag_phase) with its adjoint registered."""
+    """Forward signal model (IDEAL_model / IDEAL_mag / IDEAL_mag_phase) with its adjoint registered.  flags & F_FLAT: the
+    result is channel-interleaved, (nb, H, W, 2 ne) = data.A_from_MEBCRN(IDEAL_op(maps)) in one kernel (train-sup.py:242-244)."""
     tab, ne = _tables(te, field, maps.device)
     _check_batch(tab.shape[0], maps.shape[0])
     return _IdealForward.apply(maps, tab, model, ne, float(r2_sc), int(flags))

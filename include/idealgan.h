@@ -86,7 +86,7 @@ size_t ig_loss_scratch_bytes(int nb, int nv);
 
 /* ---- forward models: IDEAL_model / IDEAL_mag / IDEAL_mag_phase (IDEAL_model.py:220-299,404-509) */
 /* maps_d layout by model (see top); rows_or_ch = rows (WFPM: 3|4, FFPD: 3) or channels (MAGPHA: 3|4).
- * out_d: (nb, ne, nv, 2). */
+ * out_d: (nb, ne, nv, 2), or with IG_F_FLAT the channel-interleaved (nb, nv, 2 ne) of data.A_from_MEBCRN (forward only). */
 int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
                  float r2_sc, int flags, float *out_d, void *stream);
 /* adjoint: gout_d (nb, ne, nv, 2) upstream -> gmaps_d (same shape as maps, every element written) */

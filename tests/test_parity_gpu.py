@@ -369,6 +369,31 @@ def test_layout_adapters_vs_reference_vectors(golden):
         layout.B_to_MEBCRN(dev(g["to_All_in"]), mode="WF")
 
 
+@pytest.mark.parametrize("model", ["wfpm", "ffpd", "magpha"])
+@pytest.mark.parametrize("hw", [(9, 7), (40, 48)])
+def test_forward_with_interleaved_output_equals_adapter_of_planar_output(model, hw):
+    """IG_F_FLAT on the forward models = A_from_MEBCRN folded into the store (train-sup.py:242-244): bit-identical values."""
+    from idealgan import layout
+    rng = np.random.default_rng(3)
+    H, W = hw
+    nb, ne = 2, 6
+    maps = {"wfpm": lambda: synth.wfpm_maps(nb, H, W, rng, bipolar=True), "ffpd": lambda: synth.ffpd_maps(nb, H, W, rng),
+            "magpha": lambda: synth.magpha_maps(nb, H, W, rng, bipolar=True)}[model]()
+    tab = ops.gen_tables(dev(synth.te_random(nb, ne, rng)), 1.5)
+    planar = ops.ideal_fwd(MODELS[model], dev(maps), tab, ne)
+    flat = ops.ideal_fwd(MODELS[model], dev(maps), tab, ne, flags=L.F_FLAT)
+    assert flat.shape == (nb, H, W, 2 * ne)
+    assert torch.equal(flat, layout.A_from_MEBCRN(planar))
+    # autograd through the interleaved form = adapter adjoint + model adjoint
+    from idealgan import torch_ops as TO
+    te = dev(synth.te_random(nb, ne, np.random.default_rng(4)))
+    m1, m2 = dev(maps).requires_grad_(True), dev(maps).requires_grad_(True)
+    up = torch.randn((nb, H, W, 2 * ne), device="cuda")
+    (g1,) = torch.autograd.grad((TO.ideal_forward(MODELS[model], m1, te, flags=L.F_FLAT) * up).sum(), [m1])
+    (g2,) = torch.autograd.grad((layout.A_from_MEBCRN(TO.ideal_forward(MODELS[model], m2, te)) * up).sum(), [m2])
+    assert torch.equal(g1, g2)
+
+
 @pytest.mark.parametrize("shape", [(3, 5, 9, 7), (2, 6, 384, 384), (1, 16, 33, 65), (2, 1, 40, 40)])
 def test_acq_relayout_round_trip_and_adjoint(shape):
     """Ragged tiles, every echo count class, BASELINE-size slices; autograd backward is the inverse adapter."""

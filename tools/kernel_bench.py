@@ -77,6 +77,8 @@ def main():
     up_rho = torch.randn((nb, 2, H, W, 2), device=dev)
     add("ig_gen_tables", "C2", nb, nv, ne, 0, lambda: ops.gen_tables(te, 1.5))
     add("ig_ideal_fwd[wfpm]", "C1/C3 forward", nb, nv, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
+    add("ig_ideal_fwd[wfpm,flat]", "forward with interleaved output", nb, nv, ne, 24 + 8 * ne,
+        lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne, flags=L.F_FLAT))
     add("ig_ideal_bwd[wfpm]", "adjoint", nb, nv, ne, 8 * ne + 24 + 24, lambda: ops.ideal_bwd(L.MODEL_WFPM, maps, tab, ne, up))
     add("ig_ideal_loss[wfpm]", "fused fwd+mask+MSE+bwd", nb, nv, ne, 8 * ne + 24 + 24, lambda: ops.ideal_loss(L.MODEL_WFPM, maps, acqs, tab))
     add("ig_get_rho_fwd", "C1 LS solve", nb, nv, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm, tab))
