@@ -223,7 +223,9 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
                     const float re = lane_get(S[e].re, l), im = lane_get(S[e].im, l);
-                    lane_set(ys[e], l, copysignf(sqrtf(fmaf(re, re, im * im)), re != 0.f ? 1.0f : -1.0f));
+                    float mag;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));
+                    lane_set(ys[e], l, copysignf(mag, re != 0.f ? 1.0f : -1.0f));
                 }
             }
         }

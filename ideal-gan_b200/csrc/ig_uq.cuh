@@ -157,20 +157,18 @@ __device__ __forceinline__ void log_i0e_and_ratio(float z, float &log_i0e, float
         om = 1.0f;
         return;
     }
-    float i0e;
+    // (warp-uniform branching around the two series was measured: slower when z is mixed within the warps, 0.584 vs 0.554 ms)
     if (z <= 8.0f) {
         // ascending series in u = z^2 / 4: all terms positive, 16 of them reach 2e-9 of I0(8); no exponential needed for the ratio
         const float u = 0.25f * z * z;
         const float i0 = horner(kI0S, u);
-        om = 1.0f - 0.5f * z * horner(kI1S, u) / i0;
+        om = 1.0f - __fdividef(0.5f * z * horner(kI1S, u), i0);
         log_i0e = __logf(i0) - z;
-        return;
     } else {
-        const float inv = 1.0f / z, t = fmaf(16.0f, inv, -1.0f);
-        i0e = horner(kI0Bm, t) * rsqrtf(z);
+        const float inv = __fdividef(1.0f, z), t = fmaf(16.0f, inv, -1.0f);      // SFU reciprocal: 1-2 ulp, far inside the fit's own 1e-7
         om = horner(kOMBm, t) * inv;
+        log_i0e = __logf(horner(kI0Bm, t) * rsqrtf(z));
     }
-    log_i0e = __logf(i0e);
 }
 
 // One (echo, voxel) term of the Rician objective and its derivatives.  y = |A_e| observed, nu = |S_hat_e| (0 where masked),
@@ -187,7 +185,7 @@ __device__ __forceinline__ float rician_echo(float te, float a2, float y, float 
     const float var = fmaf(er, s_r, vphi) * a2;
     const bool gate = var >= kVarFloor;
     const float s2 = gate ? var : kVarFloor;
-    const float inv = 1.0f / s2;
+    const float inv = __fdividef(1.0f, s2);
     const float nu = keep ? nu_unmasked : 0.f;
     const float z = y * nu * inv;
     float li0e, om;
