@@ -99,3 +99,41 @@ class AsyncLossReducer:
     def last(self):
         self.drain()
         return self.bufs[self.step % len(self.bufs)]
+
+
+def synthesize_to_host(model, maps_host, te, out_host=None, field=1.5, r2_sc=200.0, chunk_nb=256, flags=0, device=None):
+    """Physics decoding of a shard that does not fit (or is not wanted) on the device in one piece -- config 5, the PI-VAE / LDM
+    dataset synthesis of gen_LDM_dataset.py:140-254, whose 16 384 x 384 x 384 x 6 echoes are 116 GB.  `maps_host` (pinned CPU
+    tensor, this rank's shard) is streamed through the forward kernel in chunks of `chunk_nb` samples on two alternating CUDA
+    streams, so that the host->device copy of chunk k + 1, the kernel of chunk k and the device->host copy of chunk k - 1 overlap;
+    the result lands in `out_host` (pinned; allocated if None).  `te`: (nb, ne[, 1]) echo times of the shard.  No collective:
+    ranks are independent (shard with `shard()` first)."""
+    from . import _lib as L
+    from . import ops
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    nb = maps_host.shape[0]
+    te = torch.as_tensor(te, dtype=torch.float32)
+    if te.dim() == 3:
+        te = te[:, :, 0]
+    ne = te.shape[1]
+    H, W = maps_host.shape[2], maps_host.shape[3]          # (nb, rows, H, W, ch) for every model
+    shape = (nb, H, W, 2 * ne) if flags & L.F_FLAT else (nb, ne, H, W, 2)
+    if out_host is None:
+        out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+    if tuple(out_host.shape) != shape:
+        raise ValueError(f"out_host must be {shape}, got {tuple(out_host.shape)}")
+    streams = [torch.cuda.Stream(device) for _ in range(2)]
+    keep = [None, None]                                   # device buffers of the chunk in flight on each stream
+    te_dev = te.to(device)
+    for k, start in enumerate(range(0, nb, chunk_nb)):
+        stop = min(start + chunk_nb, nb)
+        st = streams[k % 2]
+        with torch.cuda.stream(st):
+            m = maps_host[start:stop].to(device, non_blocking=True)
+            tab = ops.gen_tables(te_dev[start:stop].contiguous(), field)
+            sig = ops.ideal_fwd(model, m, tab, ne, r2_sc, flags)
+            out_host[start:stop].copy_(sig, non_blocking=True)
+            keep[k % 2] = (m, tab, sig)                   # freed when this stream's next chunk replaces them (stream-ordered allocator)
+    for st in streams:
+        st.synchronize()
+    return out_host

@@ -248,3 +248,19 @@ def test_pdff_extract(mode):
     out = ops.pdff_extract(dev(rho), mode)
     assert_close(host(out), ref.numpy(), 2e-6)
     assert (host(out)[rho[:, 0, :, :, 0] == 0] == 0).all()                              # background: 0 / 0 -> 0
+
+
+def test_chunked_synthesis_to_host_matches_one_shot():
+    """Config 5 (gen_LDM_dataset): a shard streamed through the forward kernel in chunks on two streams equals the one-shot call."""
+    from idealgan import dist as igdist
+    from idealgan import ops, synth
+    from idealgan import _lib as L
+    rng = np.random.default_rng(8)
+    nb, H, W, ne = 7, 32, 32, 6
+    maps = synth.ffpd_maps(nb, H, W, rng)
+    te = synth.te_random(nb, ne, rng)
+    want = ops.ideal_fwd(L.MODEL_FFPD, torch.from_numpy(maps).cuda(), ops.gen_tables(torch.from_numpy(te).cuda(), 1.5), ne)
+    got = igdist.synthesize_to_host(L.MODEL_FFPD, torch.from_numpy(maps).pin_memory(), te, chunk_nb=3)
+    assert got.is_pinned() and torch.equal(got, want.cpu())
+    flat = igdist.synthesize_to_host(L.MODEL_FFPD, torch.from_numpy(maps).pin_memory(), te, chunk_nb=2, flags=L.F_FLAT)
+    assert torch.equal(flat, want.permute(0, 2, 3, 1, 4).reshape(nb, H, W, 2 * ne).cpu())
