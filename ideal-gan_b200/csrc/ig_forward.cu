@@ -47,19 +47,7 @@ template <typename V> __device__ __forceinline__ void st_row(float *g_b, int row
     st_cx(g_b + static_cast<size_t>(row) * nv * 2, v0, z);
 }
 
-// STAGED: the thread's map data sit in its own 16-byte slots of a shared-memory stage (slot[k * kThreads], k = ne + chunk),
-// prefetched there with cp.async by ideal_loss_pipe_kernel; otherwise they are read from global memory.
-template <typename V, int MODEL, bool STAGED = false>
-__device__ __forceinline__ Voxel<V> decode(const float *maps_b, int rows_or_ch, int nv, int v0, int flags, const float4 *slot = nullptr, int ne = 0) {
-    static_assert(!STAGED || std::is_same<V, pk>::value, "staged sources hold two voxels per thread");
-    [[maybe_unused]] auto ld_row = [&](const float *base, int row, int, int) -> cx<V> {
-        if constexpr (STAGED) {
-            const float4 t = slot[(ne + row) * kThreads];
-            return cx<V>{mk(t.x, t.z), mk(t.y, t.w)};
-        } else {
-            return ld_cx(base + static_cast<size_t>(row) * nv * 2, v0, V{});
-        }
-    };
+template <typename V, int MODEL> __device__ __forceinline__ Voxel<V> decode(const float *maps_b, int rows_or_ch, int nv, int v0, int flags) {
     Voxel<V> x;
     const V zero = splat<V>(0.f);
     x.bturn = zero;
@@ -68,15 +56,15 @@ __device__ __forceinline__ Voxel<V> decode(const float *maps_b, int rows_or_ch, 
     x.uW = cx<V>{zero, zero};
     x.uF = cx<V>{zero, zero};
     if constexpr (MODEL == IG_MODEL_WFPM) {
-        const cx<V> m0 = ld_row(maps_b, 0, nv, v0), m1 = ld_row(maps_b, 1, nv, v0), m2 = ld_row(maps_b, 2, nv, v0);
+        const cx<V> m0 = ld_row<V>(maps_b, 0, nv, v0), m1 = ld_row<V>(maps_b, 1, nv, v0), m2 = ld_row<V>(maps_b, 2, nv, v0);
         x.rhoW = cx<V>{vmul(kRhoSc, m0.re), vmul(kRhoSc, m0.im)};
         x.rhoF = cx<V>{vmul(kRhoSc, m1.re), vmul(kRhoSc, m1.im)};
         x.phi_t = m2.re;
         x.r2raw = m2.im;
         x.r2 = (flags & IG_F_NO_RELU) ? m2.im : vrelu(m2.im);
-        if (rows_or_ch > 3) x.bturn = vmul(0.5f, ld_row(maps_b, rows_or_ch - 1, nv, v0).re);   // pi * b / (2 pi)
+        if (rows_or_ch > 3) x.bturn = vmul(0.5f, ld_row<V>(maps_b, rows_or_ch - 1, nv, v0).re);   // pi * b / (2 pi)
     } else if constexpr (MODEL == IG_MODEL_FFPD) {
-        const cx<V> m0 = ld_row(maps_b, 0, nv, v0), m1 = ld_row(maps_b, 1, nv, v0), m2 = ld_row(maps_b, 2, nv, v0);
+        const cx<V> m0 = ld_row<V>(maps_b, 0, nv, v0), m1 = ld_row<V>(maps_b, 1, nv, v0), m2 = ld_row<V>(maps_b, 2, nv, v0);
         x.ff = m0.re;
         x.pd = m1.re;
         x.r2raw = x.r2 = m1.im;
@@ -93,10 +81,7 @@ __device__ __forceinline__ Voxel<V> decode(const float *maps_b, int rows_or_ch, 
             const float *r0 = maps_b + (static_cast<size_t>(v0) + l) * rows_or_ch;
             const float *r1 = r0 + static_cast<size_t>(nv) * rows_or_ch;
             float a0, a1, a2, b0, b1, b2, b3 = 0.f;
-            if constexpr (STAGED) {            // 4-channel rows only: chunk ne + 2 row + voxel
-                const float4 p = slot[(ne + l) * kThreads], q = slot[(ne + 2 + l) * kThreads];
-                a0 = p.x; a1 = p.y; a2 = p.z; b0 = q.x; b1 = q.y; b2 = q.z; b3 = q.w;
-            } else if (rows_or_ch == 4) {
+            if (rows_or_ch == 4) {
                 const float4 p = __ldcs(reinterpret_cast<const float4 *>(r0)), q = __ldcs(reinterpret_cast<const float4 *>(r1));
                 a0 = p.x; a1 = p.y; a2 = p.z; b0 = q.x; b1 = q.y; b2 = q.z; b3 = q.w;
             } else {
@@ -171,20 +156,19 @@ __device__ __forceinline__ void write_grads(float *g_b, int rows_or_ch, int nv, 
 }
 
 // one thread's voxels of sample b starting at v0: decode, all echoes, write-out; returns the thread's loss partial
-template <int NE, typename V, int MODEL, int MODE, bool STAGED = false>
-__device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTab<NE> &T, int b, int v0, float2 *stile = nullptr, int spitch = 0,
-                                              const float4 *slot = nullptr) {
+template <int NE, typename V, int MODEL, int MODE>
+__device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTab<NE> &T, int b, int v0, float2 *stile = nullptr, int spitch = 0) {
     const int nv = p.nv, ne = p.ne;
     const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * p.rows_or_ch
                                                         : static_cast<size_t>(p.rows_or_ch) * nv * 2;
-    const Voxel<V> x = decode<V, MODEL, STAGED>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags, slot, ne);
+    const Voxel<V> x = decode<V, MODEL>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags);
     const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
     Adj<V> a;
     a.sg = czero<V>(); a.sgc = czero<V>(); a.tq = czero<V>(); a.q = czero<V>(); a.bq = splat<V>(0.f);
     V lsum = splat<V>(0.f);
     // issue every upstream / measurement load before the math so each thread has ne loads in flight
     cx<V> in[NE];
-    if constexpr (MODE != MODE_FWD && !STAGED) {
+    if constexpr (MODE != MODE_FWD) {
         const float *src = (MODE == MODE_BWD ? p.gout : p.acqs) + acq_b;
 #pragma unroll
         for (int e = 0; e < NE; ++e)
@@ -210,10 +194,6 @@ __device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTa
                 }
             } else {
                 cx<V> G;
-                if constexpr (STAGED) {            // the measured echo comes from the stage right where it is needed
-                    const float4 t = slot[e * kThreads];
-                    in[e] = cx<V>{mk(t.x, t.z), mk(t.y, t.w)};
-                }
                 if constexpr (MODE == MODE_BWD) {
                     G = in[e];
                 } else {
@@ -297,65 +277,6 @@ __global__ void __launch_bounds__(kThreads, MODEL == IG_MODEL_MAGPHA ? 2 : 3) id
     block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
 }
 
-// cp.async variant of the persistent objective kernel: every thread prefetches the 16-byte pieces IT will read of the next tile
-// (ne echo pieces + the map rows) into its own slots of a two-stage shared-memory buffer while it computes the current tile, so
-// no barrier is needed around the stages, the ne + rows loads of a tile stay in flight through the whole math of the previous
-// one, and the 24 registers that held the hoisted echoes are free.
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int NE, int MODEL>
-__global__ void __launch_bounds__(kThreads, 2) ideal_loss_pipe_kernel(const FwdParams p) {
-    __shared__ SampleTab<NE> T;
-    extern __shared__ float4 pipe[];                   // [2 stages][ne + map chunks][kThreads]
-    const int ne = p.ne, nv = p.nv;
-    const int mch = MODEL == IG_MODEL_MAGPHA ? 4 : p.rows_or_ch;
-    const int npl = ne + mch;
-    const int tiles_ps = (nv + kThreads * 2 - 1) / (kThreads * 2);
-    const long total = static_cast<long>(p.nb) * tiles_ps;
-    const int tile0 = static_cast<int>(total * blockIdx.x / gridDim.x), tile_end = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
-    const size_t map_elems = (MODEL == IG_MODEL_MAGPHA) ? static_cast<size_t>(2) * nv * 4 : static_cast<size_t>(p.rows_or_ch) * nv * 2;
-    auto issue = [&](int tile, int stage) {
-        if (tile < tile_end) {
-            const int b = tile / tiles_ps;
-            const int v0 = ((tile - b * tiles_ps) * kThreads + threadIdx.x) * 2;
-            if (v0 < nv) {
-                float4 *dst = pipe + static_cast<size_t>(stage) * npl * kThreads + threadIdx.x;
-                const float *a = p.acqs + (static_cast<size_t>(b) * ne * nv + v0) * 2;
-                for (int e = 0; e < ne; ++e) cp_async16(dst + e * kThreads, a + static_cast<size_t>(e) * nv * 2);
-                const float *m = p.maps + b * map_elems;
-                if constexpr (MODEL == IG_MODEL_MAGPHA) {
-                    for (int k = 0; k < 4; ++k) cp_async16(dst + (ne + k) * kThreads, m + (static_cast<size_t>(k >> 1) * nv + v0 + (k & 1)) * 4);
-                } else {
-                    for (int r = 0; r < mch; ++r) cp_async16(dst + (ne + r) * kThreads, m + (static_cast<size_t>(r) * nv + v0) * 2);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-    issue(tile0, 0);
-    int cur_b = -1;
-    float loss_part = 0.f;
-    for (int tile = tile0, it = 0; tile < tile_end; ++tile, ++it) {
-        issue(tile + 1, (it + 1) & 1);
-        const int b = tile / tiles_ps;
-        if (b != cur_b) {
-            if (cur_b >= 0) __syncthreads();
-            stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, ne, p.r2_sc);
-            cur_b = b;
-        }
-        cp_async_wait<1>();
-        const int v0 = ((tile - b * tiles_ps) * kThreads + threadIdx.x) * 2;
-        if (v0 < nv)
-            loss_part += ideal_voxels<NE, pk, MODEL, MODE_LOSS, true>(p, T, b, v0, nullptr, 0, pipe + static_cast<size_t>(it & 1) * npl * kThreads + threadIdx.x);
-    }
-    cp_async_wait<0>();
-    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
-}
-
 // Alternative split of the same objective: one block per tile (the shape that streams at the roofline for the adjoint), each
 // block leaving its partial with a plain store, and a one-block kernel adding the partials in index order in fp64.  No atomics,
 // no fences, bit-reproducible.
@@ -419,26 +340,6 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
         if constexpr (MODE == MODE_LOSS) {
             // measured at 64 x 384 x 384 x 6: the grid + finish pair wins for the complex-row models (0.159 vs 0.165 ms), the
             // persistent kernel for mag/phase, whose 128 registers leave too few warps for the one-tile-per-block shape (0.213 vs 0.251 ms)
-            static const int pipe_all = [] { const char *e = getenv("IG_IDEAL_PIPE"); return e ? atoi(e) : 0; }();     // experiment knob
-            const bool pipe_ok = packed && p.ne <= 8 && (MODEL != IG_MODEL_MAGPHA || p.rows_or_ch == 4);
-            if (pipe_ok && (pipe_all == 1 || (pipe_all == 2 && MODEL == IG_MODEL_MAGPHA))) {
-                if constexpr (NE <= 8) {
-                    const int mch = MODEL == IG_MODEL_MAGPHA ? 4 : p.rows_or_ch;
-                    const size_t smem = static_cast<size_t>(2) * (p.ne + mch) * kThreads * sizeof(float4);
-                    auto kern = ideal_loss_pipe_kernel<NE, MODEL>;
-                    IG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    int dev = 0, sms = 0, occ = 0;
-                    IG_CUDA(cudaGetDevice(&dev));
-                    IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-                    const long tiles = static_cast<long>(p.nb) * ((p.nv + kThreads * 2 - 1) / (kThreads * 2));
-                    long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
-                    if (g > tiles) g = tiles;
-                    kern<<<static_cast<int>(g), kThreads, smem, st>>>(p);
-                    IG_CUDA(cudaGetLastError());
-                    return 0;
-                }
-            }
             if (MODEL != IG_MODEL_MAGPHA) {
                 const dim3 g = grid_for(p.nb, p.nv, packed ? 2 : 1);
                 if (packed) ideal_loss_grid_kernel<NE, pk, MODEL><<<g, kThreads, 0, st>>>(p);
