@@ -1138,9 +1138,9 @@ static long ring_tiles(int nb, int nv) { return static_cast<long>(nb) * ((nv + 8
 template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const SolveParams &p, cudaStream_t st) {
     constexpr int kBudget = 216 * 1024;
     const int nb = p.nb, ne = p.ne, nv = p.nv;
-    auto go = [&](auto st_c, auto minb_c, auto mode_c) {
+    auto go = [&](auto st_c, auto minb_c, auto mode_c, auto ncw_c) {
         constexpr int S = decltype(st_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
-        constexpr int C = 8, W = 8;
+        constexpr int C = 8, W = decltype(ncw_c)::value;
         using Cfg = TmaCfg<NE, S, C, UQ>;
         constexpr bool exact_ok = NE <= 8;
         CUtensorMap ma{}, mp{};
@@ -1159,13 +1159,14 @@ template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const So
     using I3 = std::integral_constant<int, 3>;
     // up to 8 echoes y (and d^2) stay in registers between the two passes (95 registers at NE = 6, no spills);
     // beyond that y is parked in the thread's own 16 bytes of the stage
+    using W8 = std::integral_constant<int, 8>;
     if constexpr (NE <= 8) {
-        if (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{});
-        return go(I2{}, I2{}, I1{});
+        if (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{}, W8{});
+        return go(I2{}, I2{}, I1{}, W8{});
     } else if constexpr (!UQ) {
-        if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{});
-        if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{});
-        return go(I3{}, I1{}, I0{});
+        if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{}, W8{});
+        if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{}, W8{});
+        return go(I3{}, I1{}, I0{}, W8{});
     } else {
         set_error("uncertainty-aware ring kernel: more than 8 echoes");
         return IG_E_UNSUPPORTED;
