@@ -204,6 +204,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    try:                                                  # keep this rank (and the pinned buffers it allocates) next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception as e:                                # not fatal: affinity only matters for the host-buffer leg on multi-socket hosts
+        log(f"bench.py: CPU affinity not set ({e!r})")
     dist = None
     if world > 1:
         import torch.distributed as dist
