@@ -38,6 +38,16 @@ def test_argument_validation_without_gpu():
     assert lib.ig_ideal_fwd(0, p, 5, p, 1, 6, 16, 200.0, 0, p, 0) == -1      # rows = 5 is no WF-PM tensor
     assert lib.ig_a2a_loss(p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, 0, 0, p, p, 8, 0) == -4   # scratch too small
     assert lib.ig_get_rho_fwd(p, p, 0, 0, 0, p, 1, 1, 16, 200.0, 0, p, 0, 0) == -2        # LS solve needs ne >= 2
+    # uncertainty objectives: r2_mean without r2_var; too few echoes
+    assert lib.ig_a2a_uq_loss(p, p, 0, p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, p, 0, 0, 0, p, p, 1 << 20, 0) == -1
+    assert b"together" in lib.ig_last_error()
+    assert lib.ig_a2a_rician_loss(p, p, 0, p, 0, 0, p, 1, 1, 16, 200.0, 1.0, p, p, 0, 0, 0, p, p, 1 << 20, 0) == -2
+    # layout adapters: echo count, mode
+    assert lib.ig_acq_to_flat(p, 1, 0, 16, p, 0) == -2
+    assert lib.ig_maps_from_flat(p, 1, 16, 7, p, 0) == -1
+    assert lib.ig_maps_to_flat(p, 1, 16, 1, 2, 3.0, p, 0) == -1                # mag/phase needs >= 3 channels
+    # the interleaved layout is a forward-only output option
+    assert lib.ig_ideal_bwd(0, p, 3, p, 1, 6, 16, 200.0, L.F_FLAT, p, p, 0) == -5
     with pytest.raises(ValueError):
         L.check(-1, "x")
 
