@@ -1,0 +1,91 @@
+"""The TMA ring kernels (ig_a2a_loss, its materialised-output and uncertainty-aware siblings) over a sweep of shapes that
+exercises every launch branch: tensor-map tiles and bulk-copy tiles, whole and ragged last tiles, fewer tiles than resident
+blocks, echo counts that are and are not a kernel bucket, batch strides of a multi-row PM tensor.  The reference here is the
+unfused composition of the repo's own operators (ig_a2a_fwd + elementwise torch + ig_a2a_bwd), themselves held to the oracle in
+test_parity_gpu.py, so the sweep can afford BASELINE-like sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from idealgan import _lib as L
+from idealgan import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (nb, H, W, ne)
+    (1, 8, 16, 6),        # one 128-voxel row: a single, mostly out-of-range TMA box
+    (3, 16, 16, 6),       # 256 voxels: half a tile
+    (2, 32, 48, 6),       # 1536 voxels = 3 whole tiles
+    (5, 40, 48, 5),       # ragged last tile, ne below its bucket
+    (2, 30, 34, 6),       # even, not a multiple of 128: bulk-copy ring
+    (2, 50, 50, 3),       # bulk-copy ring, ragged, small ne
+    (1, 384, 384, 6),     # BASELINE slice
+    (7, 192, 192, 8),     # C3-like, ne = 8 (two ring stages)
+    (2, 64, 64, 2),       # two echoes: exact fit
+    (3, 64, 96, 7),
+    (2, 128, 128, 12),    # parked-y ring path (MODE 0)
+    (1, 96, 128, 16),
+]
+
+
+def _case(nb, H, W, ne, seed):
+    rng = np.random.default_rng(seed)
+    maps = torch.from_numpy(synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)).cuda()
+    te = torch.from_numpy(synth.te_random(nb, ne, rng, d_te_min=0.9e-3 if ne > 8 else 1.6e-3, d_te_d=0.3e-3 if ne > 8 else 1.0e-3)).cuda()
+    tab = ops.gen_tables(te, 1.5)
+    sig = ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    acqs = torch.where(sig != 0, sig + 0.02 * torch.randn(sig.shape, device="cuda", generator=g), torch.zeros_like(sig)).contiguous()
+    acqs[0, 0, H // 2, W // 2, 1] = 0.0                                  # one ragged voxel
+    pm_full = maps.clone()
+    pm_full[:, 2] *= 0.95
+    return acqs, pm_full, tab
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_ring_objective_equals_unfused_composition(shape):
+    nb, H, W, ne = shape
+    acqs, pm_full, tab = _case(nb, H, W, ne, 11 + nb + ne)
+    pm = pm_full[:, 2:3].contiguous()
+    rho, shat = ops.a2a_fwd(acqs, pm, tab)
+    masked = torch.where(acqs != 0, shat, torch.zeros_like(shat))
+    ref_loss = ((masked - acqs).double() ** 2).mean().item()
+    up = (2.0 * (masked - acqs) / acqs.numel()).contiguous()
+    _, ref_g = ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=False)
+    scale = float((acqs.double() ** 2).mean())                           # two echoes, two unknowns: the fit is exact and the
+    for want_out in (False, True):                                       # objective is rounding noise -> compare on the data's scale
+        loss, g, rho2, shat2 = ops.a2a_loss(acqs, pm, tab, want_rho=want_out, want_shat=want_out)
+        if ne == 2:
+            assert abs(loss.item() - ref_loss) <= 1e-5 * scale, (shape, want_out, loss.item(), ref_loss)
+            assert (g - ref_g).abs().max().item() <= 1e-5 * max(ref_g.abs().max().item(), scale)
+        else:
+            assert abs(loss.item() - ref_loss) <= 1e-5 * ref_loss, (shape, want_out, loss.item(), ref_loss)
+            assert_close(g.cpu().numpy(), ref_g.cpu().numpy(), 3e-5, f"grad pm {shape} outputs={want_out}")
+        if want_out:
+            assert_close(shat2.cpu().numpy(), shat.cpu().numpy(), 2e-6, "S_hat")
+            assert_close(rho2.cpu().numpy(), rho.cpu().numpy(), 2e-6, "rho")
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[3] <= 8][:8])
+def test_uq_ring_equals_plain_kernel_on_unaligned_copy(shape):
+    """The uncertainty-aware objective through the ring (128-voxel rows) and through the plain persistent kernel (forced by a
+    misaligned moment map) must agree."""
+    nb, H, W, ne = shape
+    acqs, pm_full, tab = _case(nb, H, W, ne, 23 + nb + ne)
+    pm = pm_full[:, 2:3].contiguous()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tissue = (pm_full[:, 0:1, :, :, 0:1] != 0).float()
+    pv = torch.rand((nb, 1, H, W, 1), device="cuda", generator=g) * 4e-3 * tissue
+    rv = torch.rand((nb, 1, H, W, 1), device="cuda", generator=g) * 3e-3 * tissue
+    rm = pm[..., 1:2].contiguous()
+    a = ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab, want_rho=True)
+    # a moment map that starts 8 bytes into an allocation is 8- but not 16-byte aligned: the ring declines, the plain kernel runs
+    buf = torch.empty(pv.numel() + 2, device="cuda")
+    pv_off = buf[2:].view_as(pv)
+    pv_off.copy_(pv)
+    assert pv_off.data_ptr() % 16 == 8
+    b = ops.a2a_uq_loss(acqs, pm, pv_off, rm, rv, tab, want_rho=True)
+    assert abs(a[0].item() - b[0].item()) <= 2e-6 * abs(b[0].item())
+    for x, y, what in zip(a[1:], b[1:], ("g_pm", "g_phi_var", "g_r2_mean", "g_r2_var", "rho")):
+        assert_close(x.cpu().numpy(), y.cpu().numpy(), 5e-6, what)
