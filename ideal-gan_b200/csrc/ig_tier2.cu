@@ -122,9 +122,11 @@ template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) cse_mag_
     float S[NE], y[NE], wm[NE];
     float a = 0.f, bb = 0.f, c = 0.f;
 #pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = __ldcs(p.mag + eb + static_cast<size_t>(e) * nv + v);
+#pragma unroll
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
-            S[e] = p.mag[eb + static_cast<size_t>(e) * nv + v];
             wm[e] = __expf(T.te[e] * R);
             const float t = wm[e] * S[e];
             y[e] = t * t;
@@ -153,7 +155,7 @@ template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) cse_mag_
                 const size_t o = eb + static_cast<size_t>(e) * nv + v;
                 if (p.fit) {
                     const float f = fmaf(T.a2[e], c, fmaf(T.a1[e], bb, a));
-                    p.fit[o] = f > 1e-6f ? sqrtf(f) / wm[e] : 0.f;
+                    p.fit[o] = f > 1e-6f ? __fdividef(sqrtf(f), wm[e]) : 0.f;
                 }
                 if (p.demod) {
                     if (p.r2nu) {
@@ -301,6 +303,11 @@ template <int NE> __global__ void __launch_bounds__(kThreads) pdff_unc_kernel(co
     const float r2map = r2 ? p.r2_mean[vb] : 0.f;
     const float s_phi = p.phi_var[vb] * (kFmSc * kFmSc);
     const float mu = r2map * p.r2_sc, s_r = r2 ? p.r2_var[vb] * (p.r2_sc * p.r2_sc) : 0.f;
+    // every echo load is in flight before the (long) modulator / projector arithmetic starts
+    float2 S[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = __ldcs(reinterpret_cast<const float2 *>(p.acqs) + (static_cast<size_t>(b) * ne + e) * nv + v);
     Mod<float> m[NE];
     cx<float> q_w = czero<float>(), q_f = czero<float>();          // M^+ Wm
 #pragma unroll
@@ -325,9 +332,9 @@ template <int NE> __global__ void __launch_bounds__(kThreads) pdff_unc_kernel(co
             const cx<float> pw = caffine(q_w, T.r[e].c_re, T.r[e].c_im, q_f);          // (M M^+ Wm)_e
             const cx<float> res{wm.re - pw.re, wm.im - pw.im};                          // (P0 Wm)_e
             const cx<float> g = remod(m[e], res);                                       // Wp_e (P0 Wm)_e
-            const float2 s2 = reinterpret_cast<const float2 *>(p.acqs)[(static_cast<size_t>(b) * ne + e) * nv + v];
+            const float2 s2 = S[e];
             const float sig = V * (g.re * g.re + g.im * g.im) + V * (s2.x * s2.x + s2.y * s2.y);
-            const float w = sig != 0.f ? 1.0f / sig : 0.f;
+            const float w = sig != 0.f ? __fdividef(1.0f, sig) : 0.f;
             const cx<float> y = demod(m[e], cx<float>{s2.x, s2.y});
             const float cr = T.r[e].c_re, ci = T.r[e].c_im;
             g00 += w;
