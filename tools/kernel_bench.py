@@ -144,6 +144,21 @@ def main():
     pm1 = maps[:, 2:3].contiguous()
     add("ig_ideal_fwd[wfpm]", "C1 single slice (latency)", 1, 384 * 384, ne, 24 + 8 * ne, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
     add("ig_get_rho_fwd", "C1 single slice (latency)", 1, 384 * 384, ne, 8 * ne + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm1, tab))
+    # C1 as a latency figure: tables + forward + LS solve of ONE slice replayed from a CUDA graph (no Python between the launches)
+    te1 = torch.from_numpy(synth.te_orig(1, ne)).to(dev)
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            t1 = ops.gen_tables(te1, 1.5)
+            s1 = ops.ideal_fwd(L.MODEL_WFPM, maps, t1, ne)
+            ops.get_rho_fwd(s1, pm1, t1)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            t1 = ops.gen_tables(te1, 1.5)
+            s1 = ops.ideal_fwd(L.MODEL_WFPM, maps, t1, ne)
+            r1, _ = ops.get_rho_fwd(s1, pm1, t1)
+    add("graph[tables+fwd+solve]", "C1 single slice, CUDA-graph replay (latency)", 1, 384 * 384, ne, 144, graph.replay)
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
 
