@@ -117,7 +117,10 @@ def main():
     back = torch.empty_like(acqs)
     add("ig_acq_from_flat", "interleaved -> planar", nb, nv, ne, 16 * ne,
         lambda: L.check(lib.ig_acq_from_flat(flat.data_ptr(), nb, ne, nv, back.data_ptr(), torch.cuda.current_stream().cuda_stream), "from_flat"))
-    del flat, back
+    pm_flat = torch.stack([pm[:, 0, :, :, 1], pm[:, 0, :, :, 0]], dim=-1).contiguous()        # flat layout: (R2*, phi)
+    add("ig_get_rho_fwd[flat]", "LS solve on interleaved acquisitions", nb, nv, ne, 8 * ne + 8 + 16,
+        lambda: ops.get_rho_fwd(flat, pm_flat, tab, flags=L.F_FLAT))
+    del flat, back, pm_flat
     # C4: bipolar mag/phase fused objective
     mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
     mp[:, 1] -= 0.25
