@@ -22,6 +22,8 @@ struct SolveParams {
     const float *phi_var, *r2_mean, *r2_var;       // uncertainty-aware objective: (nb, nv) moment maps (r2_* NULL = rem_R2)
     float *g_phi_var, *g_r2_mean, *g_r2_var;
     float *loss;
+    float *pdff, *r2s;                             // get_rho epilogue: PDFF (nb, nv) and R2* [1/s] (nb, nv) maps, optional
+    int pdff_mode;
     void *scratch;
     long pm_bstride, bip_bstride;
     int nb, ne, nv, flags;
@@ -107,6 +109,26 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
             lane_set(rw.re, l, mw * ct); lane_set(rw.im, l, mw * st);
             lane_set(rf.re, l, mf * ct); lane_set(rf.im, l, mf * st);
         }
+    }
+    if (p.pdff || p.r2s) {
+        // PDFF / R2* maps straight from the registers (ROI-analysis.py:301-306,344-354; gen_LDM_dataset.py:217-218,226-227):
+        // mode 0 |F| / |W + F|, 1 |F| / (|W| + |F|), 2 magnitude-discriminated; 0/0 -> 0.  The ratio is scale-free, so rho_sc drops out.
+        V pd = splat<V>(0.f);
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            const float wr = lane_get(rw.re, l), wi = lane_get(rw.im, l), fr = lane_get(rf.re, l), fi = lane_get(rf.im, l);
+            const float wa = sqrtf(wr * wr + wi * wi), fa = sqrtf(fr * fr + fi * fi);
+            float r;
+            if (p.pdff_mode == 1) {
+                r = fa / (wa + fa);
+            } else {
+                const float wf = sqrtf((wr + fr) * (wr + fr) + (wi + fi) * (wi + fi));
+                r = (p.pdff_mode == 0 || fa >= wa) ? fa / wf : 1.0f - wa / wf;
+            }
+            lane_set(pd, l, (isnan(r) || isinf(r)) ? 0.f : r);
+        }
+        if (p.pdff) st_real(p.pdff + static_cast<size_t>(b) * nv, v0, pd);
+        if (p.r2s) st_real(p.r2s + static_cast<size_t>(b) * nv, v0, vmul(p.r2_sc, r2));
     }
     const float inv = 1.0f / kRhoSc;
     rw = cx<V>{vmul(inv, rw.re), vmul(inv, rw.im)};
@@ -1207,6 +1229,27 @@ extern "C" int ig_get_rho_fwd(const float *acqs_d, const float *pm_d, long pm_bs
     p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.bip = bip_d; p.bip_bstride = bip_bstride; p.tab = tab_d;
     p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.flags = flags; p.rho = rho_d; p.demod = demod_d;
     const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, bip_d, rho_d, demod_d});
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (flat) return launch_pair(packed, p, st, get_rho_fwd_kernel<NE, pk, true>, get_rho_fwd_kernel<NE, float, true>);
+        return launch_pair(packed, p, st, get_rho_fwd_kernel<NE, pk, false>, get_rho_fwd_kernel<NE, float, false>);
+    });
+}
+
+extern "C" int ig_get_rho_maps(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride, const float *tab_d,
+                               int nb, int ne, int nv, float r2_sc, int flags, int pdff_mode, float *rho_d, float *pdff_d, float *r2s_d, void *stream) {
+    IG_REQUIRE(acqs_d && pm_d && tab_d && rho_d && (pdff_d || r2s_d), IG_E_ARG, "ig_get_rho_maps: null pointer");
+    IG_REQUIRE(pdff_mode >= 0 && pdff_mode <= 2, IG_E_ARG, "ig_get_rho_maps: pdff_mode %d", pdff_mode);
+    if (int rc = check_common("ig_get_rho_maps", nb, ne, nv, 2)) return rc;
+    const bool flat = flags & IG_F_FLAT;
+    IG_REQUIRE(!(flat && bip_d), IG_E_UNSUPPORTED, "ig_get_rho_maps: flat layout has no bipolar term");
+    IG_REQUIRE(!flat || aligned16(rho_d), IG_E_ALIGN, "ig_get_rho_maps: flat rho output must be 16-byte aligned");
+    SolveParams p{};
+    p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.bip = bip_d; p.bip_bstride = bip_bstride; p.tab = tab_d;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.flags = flags; p.rho = rho_d; p.pdff = pdff_d; p.r2s = r2s_d; p.pdff_mode = pdff_mode;
+    bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, bip_d, rho_d});
+    packed = packed && (!pdff_d || (reinterpret_cast<uintptr_t>(pdff_d) & 7u) == 0) && (!r2s_d || (reinterpret_cast<uintptr_t>(r2s_d) & 7u) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ig_ideal_bwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
     "ig_ideal_loss": (_i, [_i, _fp, _i, _fp, _fp, _i, _i, _i, _f, _i, _f, _fp, _fp, _fp, _fp, _sz, _fp]),
     "ig_get_rho_fwd": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
+    "ig_get_rho_maps": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _i, _fp, _fp, _fp, _fp]),
     "ig_get_rho_bwd": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp, _fp]),
     "ig_a2a_fwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
     "ig_a2a_bwd": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),

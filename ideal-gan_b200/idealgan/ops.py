@@ -9,6 +9,9 @@ import torch
 from . import _lib as L
 
 
+PDFF_MODES = {"complex_sum": 0, "mag_sum": 1, "mag_disc": 2}
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -143,6 +146,23 @@ def get_rho_fwd(acqs, pm, tab, r2_sc=200.0, flags=0, want_demod=False):
     L.check(L.load().ig_get_rho_fwd(acqs.data_ptr(), pm.data_ptr(), stride, bip_ptr, bip_stride, tab.data_ptr(), nb, ne, H * W,
                                     float(r2_sc), flags, rho.data_ptr(), _ptr(demod), _stream()), "ig_get_rho_fwd")
     return rho, demod
+
+
+def get_rho_maps(acqs, pm, tab, r2_sc=200.0, flags=0, pdff_mode="complex_sum"):
+    """LS solve with the PDFF and R2* maps computed in the same pass: (rho, pdff (nb,H,W), r2s (nb,H,W))."""
+    flat = bool(flags & L.F_FLAT)
+    acqs, nb, ne, H, W = _acq_dims(acqs, flat)
+    pm, stride = _pm_view(pm, nb, H, W, flat)
+    bip_ptr, bip_stride = 0, 0
+    if not flat and pm.shape[1] > 3:
+        bip_ptr, bip_stride = pm[:, -1].data_ptr(), stride
+    rho = torch.empty((nb, H, W, 4) if flat else (nb, 2, H, W, 2), dtype=torch.float32, device=acqs.device)
+    pdff = torch.empty((nb, H, W), dtype=torch.float32, device=acqs.device)
+    r2s = torch.empty((nb, H, W), dtype=torch.float32, device=acqs.device)
+    L.check(L.load().ig_get_rho_maps(acqs.data_ptr(), pm.data_ptr(), stride, bip_ptr, bip_stride, tab.data_ptr(), nb, ne, H * W,
+                                     float(r2_sc), flags, PDFF_MODES[pdff_mode], rho.data_ptr(), pdff.data_ptr(), r2s.data_ptr(), _stream()),
+            "ig_get_rho_maps")
+    return rho, pdff, r2s
 
 
 def get_rho_bwd(acqs, pm, tab, g_rho, g_demod, r2_sc=200.0, flags=0, need_acqs=True):
@@ -361,7 +381,6 @@ def pdff_unc(acqs, phi_mean, phi_var, r2_mean, r2_var, tab, r2_sc=200.0):
     return rho, cov
 
 
-PDFF_MODES = {"complex_sum": 0, "mag_sum": 1, "mag_disc": 2}
 
 
 def pdff_extract(rho, mode="complex_sum"):

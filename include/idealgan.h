@@ -107,6 +107,12 @@ int ig_ideal_loss(int model, const float *maps_d, int rows_or_ch, const float *a
 int ig_get_rho_fwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
                    const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, float *rho_d,
                    float *demod_d, void *stream);
+/* the same solve with the PDFF / R2* map extraction its inference callers run next (ROI-analysis.py:301-306,344-354;
+ * gen_LDM_dataset.py:217-218,226-227) as an epilogue on the registers: pdff_d (nb, nv) with pdff_mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|),
+ * 2 magnitude-discriminated (0/0 -> 0); r2s_d (nb, nv) = R2* map x r2_sc.  Either map may be NULL, not both. */
+int ig_get_rho_maps(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,
+                    const float *tab_d, int nb, int ne, int nv, float r2_sc, int flags, int pdff_mode, float *rho_d,
+                    float *pdff_d, float *r2s_d, void *stream);
 /* adjoint; g_rho_d / g_demod_d upstream (either may be NULL), outputs g_acqs_d (optional), g_pm_d (nb, nv, 2)
  * dense (row layout of pm, without the batch stride), g_bip_d (optional, (nb, nv, 2), channel 1 = 0). */
 int ig_get_rho_bwd(const float *acqs_d, const float *pm_d, long pm_bstride, const float *bip_d, long bip_bstride,

@@ -264,3 +264,24 @@ def test_chunked_synthesis_to_host_matches_one_shot():
     assert got.is_pinned() and torch.equal(got, want.cpu())
     flat = igdist.synthesize_to_host(L.MODEL_FFPD, torch.from_numpy(maps).pin_memory(), te, chunk_nb=2, flags=L.F_FLAT)
     assert torch.equal(flat, want.permute(0, 2, 3, 1, 4).reshape(nb, H, W, 2 * ne).cpu())
+
+
+@pytest.mark.parametrize("mode", ["complex_sum", "mag_sum", "mag_disc"])
+@pytest.mark.parametrize("hw", [(9, 7), (32, 48)])
+def test_get_rho_with_pdff_epilogue_equals_two_passes(mode, hw):
+    """ig_get_rho_maps = get_rho followed by the PDFF / R2* extraction of ROI-analysis.py:301-306,344-354, in one kernel."""
+    rng = np.random.default_rng(12)
+    H, W = hw
+    nb, ne = 2, 6
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+    te = synth.te_random(nb, ne, rng)
+    tab = ops.gen_tables(torch.from_numpy(te).cuda(), 1.5)
+    acqs = ops.ideal_fwd(L.MODEL_WFPM, torch.from_numpy(maps).cuda(), tab, ne)
+    acqs = acqs + 0.02 * torch.randn_like(acqs) * (acqs != 0)
+    pm = torch.from_numpy(np.ascontiguousarray(maps[:, 2:3])).cuda()
+    rho_ref, _ = ops.get_rho_fwd(acqs, pm, tab)
+    rho, pdff, r2s = ops.get_rho_maps(acqs, pm, tab, pdff_mode=mode)
+    assert torch.equal(rho, rho_ref)
+    assert_close(pdff.cpu().numpy(), ops.pdff_extract(rho_ref, mode).cpu().numpy(), 2e-6, "pdff")
+    assert_close(pdff.cpu().numpy(), orc.pdff_extract(rho_ref.cpu(), mode).numpy(), 1e-5, "pdff vs oracle")
+    assert torch.equal(r2s, pm[:, 0, :, :, 1] * 200.0)
