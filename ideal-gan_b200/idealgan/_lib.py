@@ -59,6 +59,9 @@ SIGNATURES = {
     "ig_acq_unc_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
     "ig_pdff_unc": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _f, _fp, _fp, _fp]),
     "ig_pdff_extract": (_i, [_fp, _i, _i, _i, _fp, _fp]),
+    "ig_mag_regs_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ig_mag_regs": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _f, _f, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, _fp]),
+    "ig_roi_maps": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp]),
     "ig_acq_to_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
     "ig_acq_from_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
     "ig_maps_to_flat": (_i, [_fp, _i, _i, _i, _i, _f, _fp, _fp]),

@@ -392,3 +392,64 @@ def pdff_extract(rho, mode="complex_sum"):
     out = torch.empty((nb, H, W), dtype=torch.float32, device=rho.device)
     L.check(L.load().ig_pdff_extract(rho.data_ptr(), nb, H * W, PDFF_MODES[mode], out.data_ptr(), _stream()), "ig_pdff_extract")
     return out
+
+
+_reg_scratch = {}
+
+
+def mag_regs(ls=None, demod=None, r2=None, weights=(0.0, 0.0, 0.0, 0.0), want_grads=True):
+    """Regularisers of train-IDEAL-mag.py:288-289,308-316 in one pass (ig_mag_regs).
+
+    ls (nb,3,H,W,1) fit coefficients, demod (nb,ne,H,W,1) demodulated echoes, r2 (nb,1,H,W,1) or (nb,H,W,1) R2* map
+    (any may be None).  weights = (A_demod_TV_weight, LS_NZ_weight, LS_cond_weight, R2_TV_weight).
+    Returns (sums[5] = Ad_TV, LS_NZ, WF_NZ, LS_cond, R2_TV, g_ls, g_demod, g_r2): gradients of the weighted sum."""
+    ref = next((t for t in (ls, demod, r2) if t is not None), None)
+    if ref is None:
+        raise ValueError("mag_regs: at least one of ls, demod, r2 is needed")
+    ls = None if ls is None else _chk(ls, "ls", 5)
+    demod = None if demod is None else _chk(demod, "demod", 5)
+    r2 = None if r2 is None else _chk(r2, "r2")
+    nb = ref.shape[0]
+    H, W = (ls if ls is not None else demod).shape[2:4] if (ls is not None or demod is not None) else r2.shape[-3:-1]
+    ne = 0
+    if ls is not None and tuple(ls.shape) != (nb, 3, H, W, 1):
+        raise ValueError(f"ls must be (nb, 3, H, W, 1), got {tuple(ls.shape)}")
+    if demod is not None:
+        ne = demod.shape[1]
+        if tuple(demod.shape) != (nb, ne, H, W, 1):
+            raise ValueError(f"demod must be (nb, ne, {H}, {W}, 1), got {tuple(demod.shape)}")
+    if r2 is not None and (r2.numel() != nb * H * W or r2.shape[0] != nb or r2.shape[-1] != 1):
+        raise ValueError(f"r2 must hold one (H, W, 1) map per sample, got {tuple(r2.shape)}")
+    if len(weights) != 4:
+        raise ValueError("weights = (A_demod_TV_weight, LS_NZ_weight, LS_cond_weight, R2_TV_weight)")
+    lib = L.load()
+    need = lib.ig_mag_regs_scratch_bytes(nb, H, W)
+    key = (ref.device.index, _stream())
+    buf = _reg_scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=ref.device)
+        _reg_scratch[key] = buf
+    sums = torch.empty(5, dtype=torch.float32, device=ref.device)
+    g = [torch.empty_like(t) if (t is not None and want_grads) else None for t in (ls, demod, r2)]
+    L.check(lib.ig_mag_regs(_ptr(ls), _ptr(demod), _ptr(r2), nb, ne, H, W, *(float(w) for w in weights), sums.data_ptr(),
+                            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), buf.data_ptr(), buf.numel(), _stream()), "ig_mag_regs")
+    return sums, g[0], g[1], g[2]
+
+
+ROI_MODES = {None: 0, "PDFF-var": 1, "PDFF-var-Mag": 2}
+
+
+def roi_maps(maps, var=None, mode=None):
+    """ROI-analysis.py:301-322: maps (nb,3,H,W,2) [, var (nb,5,H,W,2)] -> (nb,H,W,4|5) = |W|, |F|, |W+F|, R2* [, PDFF variance]."""
+    maps = _chk(maps, "maps", 5)
+    nb, rows, H, W, ch = maps.shape
+    if rows != 3 or ch != 2:
+        raise ValueError(f"maps must be (nb, 3, H, W, 2), got {tuple(maps.shape)}")
+    m = ROI_MODES[mode]
+    if m:
+        var = _chk(var, "var", 5)
+        if tuple(var.shape) != (nb, 5, H, W, 2):
+            raise ValueError(f"var must be (nb, 5, {H}, {W}, 2), got {tuple(var.shape)}")
+    out = torch.empty((nb, H, W, 5 if m else 4), dtype=torch.float32, device=maps.device)
+    L.check(L.load().ig_roi_maps(maps.data_ptr(), _ptr(var) if m else 0, nb, H * W, m, out.data_ptr(), _stream()), "ig_roi_maps")
+    return out

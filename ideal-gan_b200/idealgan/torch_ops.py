@@ -294,3 +294,42 @@ def pdff_uncertainty(acqs, phi_mean, phi_var, r2_mean, r2_var, te, r2_sc=200.0):
     _check_batch(tab.shape[0], acqs.shape[0])
     with torch.no_grad():
         return ops.pdff_unc(acqs.detach(), phi_mean, phi_var, r2_mean, r2_var, tab, r2_sc)
+
+
+class _MagRegs(torch.autograd.Function):
+    """One kernel gives the four sums and the gradient of their weighted sum; backward scales by the upstream on `total`."""
+
+    @staticmethod
+    def forward(ctx, ls, demod, r2, weights):
+        sums, g_ls, g_demod, g_r2 = ops.mag_regs(None if ls is None else ls.detach(), None if demod is None else demod.detach(),
+                                                 None if r2 is None else r2.detach(), weights)
+        w = torch.tensor([weights[0], weights[1], 0.0, weights[2], weights[3]], dtype=torch.float32, device=sums.device)
+        ctx.save_for_backward(*[t for t in (g_ls, g_demod, g_r2) if t is not None])
+        ctx.present = [t is not None for t in (g_ls, g_demod, g_r2)]
+        ctx.shapes = [None if t is None else t.shape for t in (ls, demod, r2)]
+        ctx.mark_non_differentiable(sums)
+        return (sums * w).sum(), sums
+
+    @staticmethod
+    def backward(ctx, g_total, _g_sums):
+        saved = list(ctx.saved_tensors)
+        grads = []
+        for present, shape in zip(ctx.present, ctx.shapes):
+            grads.append((saved.pop(0) * g_total).reshape(shape) if present else None)
+        return grads[0], grads[1], grads[2], None
+
+
+def mag_regularisers(ls=None, demod=None, r2=None, A_demod_TV_weight=0.0, LS_NZ_weight=0.0, LS_cond_weight=0.0, R2_TV_weight=0.0):
+    """The terms train-IDEAL-mag.py:308-316 (+ R2_TV :288-289) adds to G_loss, from the CSE_mag outputs.
+
+    Returns (total, logs): total = Ad_TV*w + LS_NZ*w + LS_cond*w + R2_TV*w (differentiable in ls, demod, r2) and
+    logs = dict of the unweighted sums under the names the script logs."""
+    total, sums = _MagRegs.apply(ls, demod, r2, (float(A_demod_TV_weight), float(LS_NZ_weight), float(LS_cond_weight), float(R2_TV_weight)))
+    names = ("Ad_TV", "LS_NZ", "WF_NZ", "LS_cond", "R2_TV")
+    return total, {n: sums[i] for i, n in enumerate(names)}
+
+
+def roi_maps(maps, var=None, mode=None):
+    """Inference-only map assembly / PDFF variance propagation of ROI-analysis.py:301-322."""
+    with torch.no_grad():
+        return ops.roi_maps(maps.detach(), None if var is None else var.detach(), mode)

@@ -176,6 +176,22 @@ int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const float *phi_v
 /* PDFF maps from rho (nb,2,nv,2): mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|), 2 magnitude-discriminated; 0/0 -> 0 */
 int ig_pdff_extract(const float *rho_d, int nb, int nv, int mode, float *out_d, void *stream);
 
+/* ---- script-level reductions around the magnitude fit and the ROI analysis ---- */
+/* Regularisers of train-IDEAL-mag.py:288-289,308-316 on the CSE_mag outputs, in one pass:
+ *   ls_d (nb,3,H*W) fit coefficients (a,b,c), demod_d (nb,ne,H,W) demodulated echoes, r2_d (nb,H,W) R2* map; any may be NULL.
+ *   sums_d[5] = Ad_TV, LS_NZ, WF_NZ, LS_cond, R2_TV (unweighted, as the script logs them; WF_NZ is identically 0 in
+ *   the reference: it compares A2B_ls[...,:1] with A2B_ls[...,-1:] on a last axis of length 1).
+ *   g_* (optional) = gradient of  w_ad_tv*Ad_TV + w_ls_nz*LS_NZ + w_ls_cond*LS_cond + w_r2_tv*R2_TV  w.r.t. the input.
+ * scratch_d: ig_mag_regs_scratch_bytes(nb,H,W) bytes, zero-initialised once (the kernel re-arms it). */
+size_t ig_mag_regs_scratch_bytes(int nb, int H, int W);
+int ig_mag_regs(const float *ls_d, const float *demod_d, const float *r2_d, int nb, int ne, int H, int W, float w_ad_tv,
+                float w_ls_nz, float w_ls_cond, float w_r2_tv, float *sums_d, float *g_ls_d, float *g_demod_d, float *g_r2_d,
+                void *scratch_d, size_t scratch_bytes, void *stream);
+/* Map assembly + PDFF-variance propagation of ROI-analysis.py:301-322.  maps_d (nb,3,nv,2) = W, F, (phi, R2*);
+ * var_d (nb,5,nv,2) = |C_WW|, |C_WF|, |C_FW|, |C_FF| (2nd channel 0) and (var phi, var R2*), NULL for mode 0.
+ * out_d (nb,nv,nch): |W|, |F|, |W+F|, R2* (map units) [, PDFF variance]; mode 0 nch=4, 1 general, 2 magnitude model. */
+int ig_roi_maps(const float *maps_d, const float *var_d, int nb, int nv, int mode, float *out_d, void *stream);
+
 /* ---- layout adapters: data.A_from_MEBCRN / B_from_MEBCRN / B_to_MEBCRN (data.py:262-329) ------------ */
 /* acquisitions (nb, ne, nv, 2) <-> channel-interleaved (nb, nv, 2 ne); the second is the adjoint (and inverse) of the first */
 int ig_acq_to_flat(const float *acqs_d, int nb, int ne, int nv, float *flat_d, void *stream);

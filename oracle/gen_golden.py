@@ -439,6 +439,76 @@ def gen_layout():
     save("layout", **out)
 
 
+def _reference_script_lines(script, first_tokens):
+    """Cut single statements out of a reference SCRIPT (which cannot be imported: it parses argv and builds networks) by the
+    text each starts with, in file order, dedented, for `exec` on the shim.  A token that is missing raises (reference drift)."""
+    import textwrap
+    lines = open(os.path.join(REF, script)).read().splitlines()
+    out, pos = [], 0
+    for tok in first_tokens:
+        for k in range(pos, len(lines)):
+            if lines[k].strip().startswith(tok):
+                out.append(lines[k].strip())
+                pos = k + 1
+                break
+        else:
+            raise RuntimeError(f"{script}: no statement starting with {tok!r} after line {pos}")
+    return textwrap.dedent("\n".join(out))
+
+
+def gen_regs():
+    """Regularisers of train-IDEAL-mag.py:288-289,304,308-316 and the map assembly of ROI-analysis.py:301-322: the scripts' own
+    statements executed on the shim, inputs from the reference's CSE_mag / PDFF_uncertainty on synthetic data."""
+    import types as _types
+    rng = np.random.default_rng(7)
+    out = {}
+    src = _reference_script_lines("train-IDEAL-mag.py", [
+        "R2_TV = tf.reduce_sum(tf.image.total_variation(", "G_loss += R2_TV * args.R2_TV_weight", "Ad_aux = tf.reshape(A_demod",
+        "Ad_TV = tf.reduce_sum(", "LS_NZ = tf.reduce_sum(", "WF_NZ = tf.reduce_sum(", "aux_cond = tf.square(", "LS_cond = tf.reduce_sum(",
+        "G_loss += Ad_TV * args.A_demod_TV_weight"])
+    for name, nb, ne, hh, ww in [("reg6", 2, 6, H, W), ("reg3_odd", 3, 3, 7, 9)]:
+        maps = synth.wfpm_maps(nb, hh, ww, rng, neg_r2_frac=0.0, masked=(name == "reg6"))
+        te = synth.te_orig(nb, ne)
+        with torch.no_grad():
+            acqs = synth.add_noise(N(wf.IDEAL_Layer(field=1.5)(T(maps), te=T(te))), rng)
+            if name == "reg6":
+                acqs *= (maps[:, :1, :, :, :1] != 0)
+            mag = np.sqrt((acqs ** 2).sum(-1, keepdims=True)).astype(np.float32)
+            r2 = np.ascontiguousarray(maps[:, 2:3, :, :, 1:2])
+            _, fit, demod, ls = wf.CSE_mag(T(mag), T(r2), [1.5, T(te)], demod_signal=True)
+        ls = (N(ls) + 0.05 * rng.standard_normal(tuple(ls.shape))).astype(np.float32)     # negatives and both discriminant signs
+        demod = N(demod).astype(np.float32)
+        weights = (0.3, 1.7, 0.9, 0.6)
+        a_ls, a_demod, a_r2 = T(ls, grad=True), T(demod, grad=True), T(r2, grad=True)
+        ns_ = {"tf": tf_shim, "A_demod": a_demod, "A2B_ls": a_ls, "A2B2A_mag": T(N(fit)), "R2_TV_aux": a_r2, "G_loss": 0.0,
+               "args": _types.SimpleNamespace(A_demod_TV_weight=weights[0], LS_NZ_weight=weights[1], LS_cond_weight=weights[2], R2_TV_weight=weights[3])}
+        exec(src, ns_)
+        grads = torch.autograd.grad(ns_["G_loss"], [a_ls, a_demod, a_r2])
+        out.update({f"{name}_ls": ls, f"{name}_demod": demod, f"{name}_r2": r2, f"{name}_weights": np.float32(weights),
+                    f"{name}_sums": np.float32([ns_[k].item() for k in ("Ad_TV", "LS_NZ", "WF_NZ", "LS_cond", "R2_TV")]),
+                    f"{name}_total": np.float32(ns_["G_loss"].item()),
+                    f"{name}_g_ls": N(grads[0]), f"{name}_g_demod": N(grads[1]), f"{name}_g_r2": N(grads[2])})
+
+    roi_src = _reference_script_lines("ROI-analysis.py", [
+        "A2B_WF_abs = tf.math.sqrt(", "A2B_WF_abs = tf.transpose(", "A2B_WFsum_abs = tf.math.sqrt(", "A2B_WFsum_abs = tf.transpose(",
+        "A2B_R2 = A2B[:,2,:,:,1:]", "A2B = tf.concat([A2B_WF_abs,A2B_WFsum_abs,A2B_R2],axis=-1)"])
+    var_src = _reference_script_lines("ROI-analysis.py", [
+        "W_var = tf.abs(", "WF_var = tf.abs(", "F_var = tf.abs(", "PDFF_var = W_var/(", "PDFF_var -= 2 * WF_var", "PDFF_var += (W_var + F_var",
+        "PDFF_var *= A2B_WF_abs", "A2B = tf.concat([A2B,PDFF_var],axis=-1)"])
+    nb = 2
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0, masked=False)
+    var = rng.uniform(1e-6, 1e-3, size=(nb, 5, H, W, 2)).astype(np.float32)
+    var[:, :4, :, :, 1] = 0.0                                           # ROI-analysis.py:244: covariance rows are zero-padded
+    var[0, :, :2] = 1e-10                                               # the background fill of :248
+    with torch.no_grad():
+        ns_ = {"tf": tf_shim, "A2B": T(maps), "A2B_var": T(var)}
+        exec(roi_src, ns_)
+        out.update({"roi_maps": maps, "roi_var": var, "roi_out4": N(ns_["A2B"])})
+        exec(var_src, ns_)
+        out["roi_out5"] = N(ns_["A2B"])
+    save("regs", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_tables()
@@ -449,3 +519,4 @@ if __name__ == "__main__":
     gen_uq()
     gen_rician()
     gen_layout()
+    gen_regs()

@@ -567,6 +567,55 @@ def pdff_extract(rho, mode="complex_sum"):
 
 
 # ----------------------------------------------------------------------------------------------
+# script-level reductions: train-IDEAL-mag.py:288-289,308-316 and ROI-analysis.py:301-322
+# ----------------------------------------------------------------------------------------------
+def total_variation(x):
+    """tf.image.total_variation summed over the batch: x (n, H, W, C) -> sum |x[1:] - x[:-1]| over rows and columns."""
+    return (x[:, 1:] - x[:, :-1]).abs().sum() + (x[:, :, 1:] - x[:, :, :-1]).abs().sum()
+
+
+def mag_regularisers(ls=None, demod=None, r2=None):
+    """The five sums train-IDEAL-mag.py logs (:288-289 R2_TV, :308-314 Ad_TV, LS_NZ, WF_NZ, LS_cond), unweighted.
+    ls (nb,3,H,W,1), demod (nb,ne,H,W,1), r2 (nb,1,H,W,1).  Differentiable through autograd.
+    Quirks kept: `[..., ::2]` / `[..., :1]` / `[..., -1:]` index the LAST axis (length 1), so LS_NZ runs over all
+    three coefficients and WF_NZ compares every element with itself (identically zero)."""
+    ref = next(t for t in (ls, demod, r2) if t is not None)
+    zero = torch.zeros((), dtype=ref.dtype)
+    out = {"Ad_TV": zero, "LS_NZ": zero, "WF_NZ": zero, "LS_cond": zero, "R2_TV": zero}
+    if demod is not None:
+        out["Ad_TV"] = total_variation(demod.reshape(-1, *demod.shape[2:]))
+    if r2 is not None:
+        out["R2_TV"] = total_variation(r2.reshape(r2.shape[0], *r2.shape[-3:]))
+    if ls is not None:
+        out["LS_NZ"] = torch.where(ls < 0, ls * ls, torch.zeros_like(ls)).sum()
+        q = ls[:, 1:2] ** 2 - 4.0 * ls[:, 0:1] * ls[:, 2:3]
+        out["LS_cond"] = torch.where(q > 0, q * q, torch.zeros_like(q)).sum()
+    return out
+
+
+def roi_maps(maps, var=None, mode=None):
+    """ROI-analysis.py:301-322.  maps (nb,3,H,W,2), var (nb,5,H,W,2) -> (nb,H,W,4|5): |W|, |F|, |W+F|, R2* [, PDFF variance].
+    mode None: no variance; 'PDFF-var': the propagated variance; 'PDFF-var-Mag': the W-F row (model_sel == 'Mag')."""
+    wf_abs = torch.sqrt((maps[:, :2] ** 2).sum(-1)).permute(0, 2, 3, 1)                    # (nb,H,W,2)
+    sum_abs = torch.sqrt((maps[:, :2].sum(1, keepdim=True) ** 2).sum(-1)).permute(0, 2, 3, 1)
+    out = torch.cat([wf_abs, sum_abs, maps[:, 2, :, :, 1:]], dim=-1)
+    if mode is None:
+        return out
+    w_var = torch.complex(var[:, 0, ..., :1], var[:, 0, ..., 1:]).abs()
+    wf_var = torch.complex(var[:, 1, ..., :1], var[:, 1, ..., 1:]).abs()
+    f_var = torch.complex(var[:, 3, ..., :1], var[:, 3, ..., 1:]).abs()
+    if mode == "PDFF-var-Mag":
+        pv = wf_var
+    else:
+        wa = wf_abs[..., :1]
+        pv = w_var / wa ** 2
+        pv = pv - 2 * wf_var / (wa * sum_abs)
+        pv = pv + (w_var + f_var + 2 * wf_var) / wa
+        pv = pv * (wa ** 2 / sum_abs ** 2)
+    return torch.cat([out, pv], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
 # layout adapters (data.py:262-329)
 # ----------------------------------------------------------------------------------------------
 def A_from_MEBCRN(A):

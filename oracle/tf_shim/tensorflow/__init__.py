@@ -259,6 +259,22 @@ linalg = types.SimpleNamespace(
     matvec=lambda a, b: _t.matmul(a, b.unsqueeze(-1)).squeeze(-1),
 )
 
+def reduce_prod(x, axis=None, keepdims=False):
+    if axis is None:
+        return _t.prod(x)
+    return _t.prod(x, dim=axis, keepdim=keepdims)
+
+
+def _total_variation(images, name=None):
+    """tf.image.total_variation: images (n, H, W, C) -> (n,), or (H, W, C) -> scalar; sum of absolute neighbour differences."""
+    if images.dim() == 3:
+        return (images[1:] - images[:-1]).abs().sum() + (images[:, 1:] - images[:, :-1]).abs().sum()
+    return (images[:, 1:] - images[:, :-1]).abs().sum(dim=(1, 2, 3)) + (images[:, :, 1:] - images[:, :, :-1]).abs().sum(dim=(1, 2, 3))
+
+
+image = types.SimpleNamespace(total_variation=_total_variation)
+
+
 nn = types.SimpleNamespace(relu=_t.relu)
 debugging = types.SimpleNamespace(assert_all_finite=_assert_all_finite)
 

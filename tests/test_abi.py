@@ -46,6 +46,12 @@ def test_argument_validation_without_gpu():
     assert lib.ig_acq_to_flat(p, 1, 0, 16, p, 0) == -2
     assert lib.ig_maps_from_flat(p, 1, 16, 7, p, 0) == -1
     assert lib.ig_maps_to_flat(p, 1, 16, 1, 2, 3.0, p, 0) == -1                # mag/phase needs >= 3 channels
+    # script-level reductions: nothing to reduce, gradient of an absent input, scratch, mode without variance maps
+    assert lib.ig_mag_regs(0, 0, 0, 1, 6, 4, 4, 0.0, 0.0, 0.0, 0.0, p, 0, 0, 0, p, 1 << 20, 0) == -1
+    assert lib.ig_mag_regs(p, 0, 0, 1, 6, 4, 4, 0.0, 0.0, 0.0, 0.0, p, 0, p, 0, p, 1 << 20, 0) == -1
+    assert lib.ig_mag_regs(p, 0, 0, 1, 6, 4, 4, 0.0, 0.0, 0.0, 0.0, p, 0, 0, 0, p, 8, 0) == -1
+    assert lib.ig_mag_regs_scratch_bytes(2, 384, 384) == 16 + 16 * 2 * 576
+    assert lib.ig_roi_maps(p, 0, 1, 16, 1, p, 0) == -1
     # the interleaved layout is a forward-only output option
     assert lib.ig_ideal_bwd(0, p, 3, p, 1, 6, 16, 200.0, L.F_FLAT, p, p, 0) == -5
     with pytest.raises(ValueError):

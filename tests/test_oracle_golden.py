@@ -289,6 +289,36 @@ def test_layout_adapters(golden):
         assert np.array_equal(npy(orc.B_to_MEBCRN(tt(g[f"to_{key}_in"]), mode=mode)), g[f"to_{key}_out"])
 
 
+@pytest.mark.parametrize("name", ["reg6", "reg3_odd"])
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_mag_regularisers(golden, name, rdtype, tol):
+    """train-IDEAL-mag.py:288-289,308-316 (the script's own statements, oracle/gen_golden.py:gen_regs)."""
+    g = golden("regs")
+    ls, demod, r2 = (tt(g[f"{name}_{k}"], grad=True, rdtype=rdtype) for k in ("ls", "demod", "r2"))
+    out = orc.mag_regularisers(ls, demod, r2)
+    sums = np.array([out[k].item() for k in ("Ad_TV", "LS_NZ", "WF_NZ", "LS_cond", "R2_TV")])
+    np.testing.assert_allclose(sums, g[f"{name}_sums"], rtol=2e-6 if rdtype == torch.float32 else 1e-5)
+    assert sums[2] == 0.0                                                   # the reference's WF_NZ is identically zero
+    w = g[f"{name}_weights"].astype(np.float64)
+    total = out["Ad_TV"] * w[0] + out["LS_NZ"] * w[1] + out["LS_cond"] * w[2] + out["R2_TV"] * w[3]
+    grads = torch.autograd.grad(total, [ls, demod, r2])
+    for got, key in zip(grads, ("g_ls", "g_demod", "g_r2")):
+        assert_close(npy(got), g[f"{name}_{key}"], tol, key)
+
+
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_roi_maps(golden, rdtype, tol):
+    """ROI-analysis.py:301-322."""
+    g = golden("regs")
+    maps, var = tt(g["roi_maps"], rdtype=rdtype), tt(g["roi_var"], rdtype=rdtype)
+    assert_close(npy(orc.roi_maps(maps)), g["roi_out4"], tol)
+    out5 = npy(orc.roi_maps(maps, var, "PDFF-var"))
+    assert_close(out5[..., :4], g["roi_out4"], tol)
+    assert_close(out5[..., 4], g["roi_out5"][..., 4], 10 * tol, "PDFF variance")   # three-term cancellation in fp32
+    mag = npy(orc.roi_maps(maps, var, "PDFF-var-Mag"))
+    assert_close(mag[..., 4], g["roi_var"][:, 1, :, :, 0], tol)
+
+
 def test_round_trip_and_idempotence():
     """SURVEY §8c KATs (i)-(iv) in fp64."""
     from idealgan import synth

@@ -109,7 +109,13 @@ def main():
     add("ig_pdff_unc", "PDFF_uncertainty (weighted LS per voxel)", nb, nv, ne, 8 * ne + 16 + 16 + 16,
         lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab))
     add("ig_pdff_extract", "PDFF map", nb, nv, ne, 16 + 4, lambda: ops.pdff_extract(rho_hat))
-    del mag, rho_hat
+    _, _, demod_s, ls_s, _ = ops.cse_mag_fwd(mag, r2map, tab)
+    add("ig_mag_regs", "train-IDEAL-mag regularisers (4 sums + gradients)", nb, nv, ne, 2 * (4 * ne + 12 + 4),
+        lambda: ops.mag_regs(ls_s.reshape(nb, 3, H, W, 1), demod_s.reshape(nb, ne, H, W, 1), r2map, (0.1, 0.2, 0.3, 0.4)))
+    var5 = torch.rand((nb, 5, H, W, 2), device=dev, generator=g) * 1e-3
+    add("ig_roi_maps", "ROI-analysis map assembly + PDFF variance", nb, nv, ne, 24 + 40 + 20,
+        lambda: ops.roi_maps(maps, var5, "PDFF-var"))
+    del mag, rho_hat, demod_s, ls_s, var5
     flat = torch.empty((nb, H, W, 2 * ne), device=dev)
     lib = L.load()
     add("ig_acq_to_flat", "A_from_MEBCRN (planar -> interleaved)", nb, nv, ne, 16 * ne,
