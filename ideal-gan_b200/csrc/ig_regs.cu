@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) mag_regs_kernel(RegParams p, void *s
     if (i < nv) {
         const int row = i / p.W, col = i - row * p.W;
         if (p.demod) {
+#pragma unroll 1
             for (int e = 0; e < p.ne; ++e) {
                 const size_t plane = (static_cast<size_t>(b) * p.ne + e) * nv;
                 acc[0] += tv_plane<VEC>(p.demod + plane, p.g_demod ? p.g_demod + plane : nullptr, p.w_ad_tv, row, col, p.H, p.W);
