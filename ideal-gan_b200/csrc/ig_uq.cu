@@ -174,6 +174,8 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
 // =================================================================================================
 template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a_rician_loss_kernel(const UqParams p) {
     __shared__ SampleTab<NE> T;
+    __shared__ float4 btab[kBesselRows * 3];
+    stage_bessel_table(btab);            // visible after the __syncthreads of the first stage_table
     const int nv = p.nv, ne = p.ne;
     constexpr int L = lanes<V>::n;
     const int tiles_ps = (nv + kThreads * L - 1) / (kThreads * L);
@@ -243,8 +245,8 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
                     const float a2l = lane_get(a2, l), d = lane_get(dec[e], l), ysl = lane_get(ys[e], l);
-                    const float ra = a2l > 0.f ? rsqrtf(a2l) : 0.f;
-                    const float g = rician_echo(R.te, a2l, fabsf(ysl), d * a2l * ra, !signbit(ysl), lane_get(pv, l) * fm2, lane_get(rm, l) * p.r2_sc,
+                    const float ra = a2l > 1e-30f ? rsqrt_ftz(a2l) : 0.f;
+                    const float g = rician_echo(btab, R.te, a2l, fabsf(ysl), d * a2l * ra, !signbit(ysl), lane_get(pv, l) * fm2, lane_get(rm, l) * p.r2_sc,
                                                 lane_get(rv, l) * r22, rem, acc[l]);
                     lane_set(sc, l, g * d * ra);
                 }

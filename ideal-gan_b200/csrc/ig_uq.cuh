@@ -133,51 +133,62 @@ __device__ __forceinline__ void uq_slow_voxel(const SampleTab<NE> &T, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rician objective (VarMeanSquaredErrorR2, tf2gan/loss.py:143-162): exponentially scaled Bessel functions.
-// z <= 8: the ascending power series; z > 8: Chebyshev fits of sqrt(z) i0e(z) and z (1 - I1/I0) in t = 16 / z - 1, converted to
-// monomials, generated by tools/gen_bessel_coeffs.py (fits against scipy/mpmath):
-// float32 evaluation (power series on [0, 8], Horner of the fits above): max rel err i0e 4.76e-07 on [0, 1e5], I1/I0 2.87e-07 on (0, 8], 1 - I1/I0 1.38e-07 on (8, 1e5]
+// Rician objective (VarMeanSquaredErrorR2, tf2gan/loss.py:143-162): exponentially scaled Bessel terms from a table.
+// log i0e(z) and om(z) = 1 - I1(z) / I0(z) are smooth on a logarithmic scale: the float's exponent and top two mantissa
+// bits pick one of four polynomial pieces per octave, the remaining mantissa bits are the local variable t in [0, 1).
+// 136 rows of 12 floats (degree 4 for log i0e, degree 5 for om) generated by tools/gen_bessel_coeffs.py against
+// scipy.special; float32 evaluation error 1.9e-7 / 1.8e-7 relative.  No branch on z, so no divergence between lanes
+// (the earlier power-series / asymptotic-fit pair cost ~100 scalar instructions per element in mixed warps, this ~25).
 // ------------------------------------------------------------------------------------------------
-__device__ constexpr float kI0S[16] = {1.000000000e+00f, 1.000000000e+00f, 2.500000000e-01f, 2.777777778e-02f, 1.736111111e-03f, 6.944444444e-05f, 1.929012346e-06f, 3.936759889e-08f, 6.151187327e-10f, 7.594058428e-12f, 7.594058428e-14f, 6.276081346e-16f, 4.358389823e-18f, 2.578928890e-20f, 1.315780046e-22f, 5.847911314e-25f};   // 1 / (k!)^2: I0(z) = sum_k (z^2 / 4)^k / (k!)^2
-__device__ constexpr float kI1S[16] = {1.000000000e+00f, 5.000000000e-01f, 8.333333333e-02f, 6.944444444e-03f, 3.472222222e-04f, 1.157407407e-05f, 2.755731922e-07f, 4.920949861e-09f, 6.834652585e-11f, 7.594058428e-13f, 6.903689480e-15f, 5.230067788e-17f, 3.352607556e-19f, 1.842092064e-21f, 8.771866971e-24f, 3.654944571e-26f};   // 1 / (k! (k+1)!): I1(z) = (z / 2) sum_k (z^2 / 4)^k / (k! (k+1)!)
-__device__ constexpr float kI0Bm[7] = {4.021765094e-01f, 3.360555700e-03f, 1.362171642e-04f, 1.111214829e-05f, 1.476115735e-06f, 3.626670386e-07f, 1.086794244e-07f};
-__device__ constexpr float kOMBm[10] = {5.083559127e-01f, 8.963486383e-03f, 6.828079077e-04f, 8.890689196e-05f, 1.701834676e-05f, 4.766410608e-06f, 2.530375952e-06f, 1.220925379e-06f, -2.431821501e-07f, -3.547550954e-07f};
+constexpr int kBesselRows = 136, kBesselRowBase = 468;          // rows for 2^-10 <= z < 2^24; (bits >> 21) - 4 (127 - 10)
+__device__ __align__(16) const float kBesselTab[kBesselRows * 12] = {
+#include "ig_bessel_tab.inc"
+};
 
-template <int N> __device__ __forceinline__ float horner(const float (&c)[N], float t) {
-    float acc = c[N - 1];
-#pragma unroll
-    for (int k = N - 2; k >= 0; --k) acc = fmaf(acc, t, c[k]);
-    return acc;
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-// z >= 0 -> log(i0e(z)) = log I0(z) - z, and om = 1 - I1(z) / I0(z) (fitted directly above 8: it decays like 1 / (2 z))
-__device__ __forceinline__ void log_i0e_and_ratio(float z, float &log_i0e, float &om) {
-    if (z == 0.f) {            // masked or background element: I0(0) = 1, I1(0) = 0
-        log_i0e = 0.f;
-        om = 1.0f;
-        return;
-    }
-    // (warp-uniform branching around the two series was measured: slower when z is mixed within the warps, 0.584 vs 0.554 ms)
-    if (z <= 8.0f) {
-        // ascending series in u = z^2 / 4: all terms positive, 16 of them reach 2e-9 of I0(8); no exponential needed for the ratio
-        const float u = 0.25f * z * z;
-        const float i0 = horner(kI0S, u);
-        om = 1.0f - __fdividef(0.5f * z * horner(kI1S, u), i0);
-        log_i0e = __logf(i0) - z;
-    } else {
-        const float inv = __fdividef(1.0f, z), t = fmaf(16.0f, inv, -1.0f);      // SFU reciprocal: 1-2 ulp, far inside the fit's own 1e-7
-        om = horner(kOMBm, t) * inv;
-        log_i0e = __logf(horner(kI0Bm, t) * rsqrtf(z));
-    }
+// cooperative copy of the table into shared memory (16-byte rows of a float4 array); caller synchronises
+__device__ __forceinline__ void stage_bessel_table(float4 *smem_tab) {
+    const float4 *src = reinterpret_cast<const float4 *>(kBesselTab);
+    for (int i = threadIdx.x; i < kBesselRows * 3; i += blockDim.x) smem_tab[i] = src[i];
+}
+
+// z >= 0 -> log(i0e(z)) and om = 1 - I1(z) / I0(z)
+__device__ __forceinline__ void bessel_terms(const float4 *__restrict__ tab, float z, float &log_i0e, float &om) {
+    const float zc = fminf(fmaxf(z, 0.0009765625f), 16777215.0f);
+    const unsigned bits = __float_as_uint(zc);
+    const float4 *row = tab + ((bits >> 21) - kBesselRowBase) * 3;
+    const float t = __uint_as_float(((bits << 2) & 0x007fffffu) | 0x3f800000u) - 1.0f;
+    const float4 a = row[0], b = row[1], c = row[2];
+    const float p = fmaf(fmaf(fmaf(fmaf(b.x, t, a.w), t, a.z), t, a.y), t, a.x);
+    const float q = fmaf(fmaf(fmaf(fmaf(fmaf(c.z, t, c.y), t, c.x), t, b.w), t, b.z), t, b.y);
+    const bool tiny = z < 0.0009765625f;                  // incl. z = 0 (masked / background): I0 = 1, I1 = 0
+    log_i0e = tiny ? z * fmaf(0.25f, z, -1.0f) : p;       // -z + z^2 / 4 (next term z^4 / 64)
+    om = tiny ? fmaf(-0.5f, z, 1.0f) : q;                 // 1 - z / 2   (next term z^3 / 16)
 }
 
 // One (echo, voxel) term of the Rician objective and its derivatives.  y = |A_e| observed, nu = |S_hat_e| (0 where masked),
 // var = V_e |yhat_e|^2.  With s2 = max(var, 1e-5), z = y nu / s2:
 //   -loglik = -[y > 1e-5] log y + log s2 + (y - nu)^2 / (2 s2) - log i0e(z)        ((y^2 + nu^2) / (2 s2) - z, without the cancellation)
 //   d/d nu  = ((nu - y) + y om) / s2,    d/d s2 = [var >= 1e-5] (1 - ((y - nu)^2 / 2 + y nu om) / s2) / s2,    om = 1 - I1/I0 (z)
-// Returns d/d nu (0 where masked); accumulates the loss and the moment gradients like uq_echo.
-__device__ __forceinline__ float rician_echo(float te, float a2, float y, float nu_unmasked, bool keep, float s_phi, float mu, float s_r, bool rem,
-                                             UqAcc &acc) {
+// Returns d/d nu (0 where masked); accumulates the loss and the moment gradients like uq_echo.  The two logarithms are one:
+// log s2 - [y > 1e-5] log y = log(s2 / y') with y' = y or 1.
+__device__ __forceinline__ float rician_echo(const float4 *__restrict__ btab, float te, float a2, float y, float nu_unmasked, bool keep, float s_phi,
+                                             float mu, float s_r, bool rem, UqAcc &acc) {
     const float k = kTwoPi * te, k2 = k * k;
     float ephi;
     const float vphi = one_minus_exp_neg(k2 * s_phi, ephi);
@@ -185,19 +196,21 @@ __device__ __forceinline__ float rician_echo(float te, float a2, float y, float 
     const float var = fmaf(er, s_r, vphi) * a2;
     const bool gate = var >= kVarFloor;
     const float s2 = gate ? var : kVarFloor;
-    const float inv = __fdividef(1.0f, s2);
+    const float inv = rcp_ftz(s2);
     const float nu = keep ? nu_unmasked : 0.f;
     const float z = y * nu * inv;
     float li0e, om;
-    log_i0e_and_ratio(z, li0e, om);
+    bessel_terms(btab, z, li0e, om);
     const float diff = y - nu;
-    acc.loss += __logf(s2) + 0.5f * diff * diff * inv - li0e - (y > 1e-5f ? __logf(y) : 0.f);
-    const float gv = gate ? inv * (1.0f - (0.5f * diff * diff + y * nu * om) * inv) : 0.f;
+    const float hd = 0.5f * diff * diff;
+    const float ratio = y > 1e-5f ? s2 * rcp_ftz(y) : s2;
+    acc.loss += fmaf(hd, inv, fmaf(kLn2, lg2_ftz(ratio), -li0e));
+    const float gv = gate ? inv * fmaf(-fmaf(y * nu, om, hd), inv, 1.0f) : 0.f;
     const float ga = gv * a2;
     acc.g_sphi = fmaf(ga * k2, ephi, acc.g_sphi);
     acc.g_mu = fmaf(-ga * te, er * s_r, acc.g_mu);
     acc.g_sr = fmaf(ga, er, acc.g_sr);
-    return keep ? (y * om - diff) * inv : 0.f;
+    return keep ? fmaf(y, om, -diff) * inv : 0.f;
 }
 
 // host: the same objective on the TMA ring of ig_solve.cu (IG_E_UNSUPPORTED when the shape is not covered)
