@@ -234,7 +234,14 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
         UqAcc acc[L];
 #pragma unroll
         for (int l = 0; l < L; ++l) acc[l] = UqAcc{0.f, 0.f, 0.f, 0.f};
+        UqAcc2 acc2{splat<pk>(0.f), splat<pk>(0.f), splat<pk>(0.f), splat<pk>(0.f)};
         cx<V> gw = czero<V>(), gf = czero<V>(), aw = czero<V>(), af = czero<V>();
+        [[maybe_unused]] V sp2, mu2, sr2;
+        if constexpr (L == 2) {
+            sp2 = vmul(fm2, pv);
+            mu2 = vmul(p.r2_sc, rm);
+            sr2 = vmul(r22, rv);
+        }
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
@@ -242,13 +249,20 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
                 const cx<V> yhat = caffine(rw, R.c_re, R.c_im, rf);
                 const V a2 = vfma(yhat.re, yhat.re, vmul(yhat.im, yhat.im));
                 V sc = zero;       // g_nu d / |yhat|
+                if constexpr (L == 2) {
+                    const pk ra = mk(a2.d.x > 1e-30f ? rsqrt_ftz(a2.d.x) : 0.f, a2.d.y > 1e-30f ? rsqrt_ftz(a2.d.y) : 0.f);
+                    const pk dra = vmul(dec[e], ra);
+                    const pk g = rician_echo(btab, R.te, a2, ys[e], vmul(dra, a2), sp2, mu2, sr2, rem, acc2);
+                    sc = vmul(g, dra);
+                } else {
 #pragma unroll
-                for (int l = 0; l < L; ++l) {
-                    const float a2l = lane_get(a2, l), d = lane_get(dec[e], l), ysl = lane_get(ys[e], l);
-                    const float ra = a2l > 1e-30f ? rsqrt_ftz(a2l) : 0.f;
-                    const float g = rician_echo(btab, R.te, a2l, fabsf(ysl), d * a2l * ra, !signbit(ysl), lane_get(pv, l) * fm2, lane_get(rm, l) * p.r2_sc,
-                                                lane_get(rv, l) * r22, rem, acc[l]);
-                    lane_set(sc, l, g * d * ra);
+                    for (int l = 0; l < L; ++l) {
+                        const float a2l = lane_get(a2, l), d = lane_get(dec[e], l), ysl = lane_get(ys[e], l);
+                        const float ra = a2l > 1e-30f ? rsqrt_ftz(a2l) : 0.f;
+                        const float g = rician_echo(btab, R.te, a2l, fabsf(ysl), d * a2l * ra, !signbit(ysl), lane_get(pv, l) * fm2,
+                                                    lane_get(rm, l) * p.r2_sc, lane_get(rv, l) * r22, rem, acc[l]);
+                        lane_set(sc, l, g * d * ra);
+                    }
                 }
                 const cx<V> v = cscale(sc, yhat);
                 gw.re = vadd(gw.re, v.re);
@@ -258,6 +272,10 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
                 aw.im = vfma(R.te, v.im, aw.im);
                 cmac(af, R.te * R.c_re, -R.te * R.c_im, v);
             }
+        }
+        if constexpr (L == 2) {
+            acc[0] = UqAcc{acc2.g_sphi.d.x, acc2.g_mu.d.x, acc2.g_sr.d.x, acc2.loss.d.x};
+            acc[1] = UqAcc{acc2.g_sphi.d.y, acc2.g_mu.d.y, acc2.g_sr.d.y, acc2.loss.d.y};
         }
         cx<V> X = cmulc(gw, tw);
         const cx<V> x1 = cmulc(gf, tf), x2 = cmulc(aw, rw), x3 = cmulc(af, rf);

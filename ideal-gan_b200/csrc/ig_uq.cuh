@@ -213,6 +213,49 @@ __device__ __forceinline__ float rician_echo(const float4 *__restrict__ btab, fl
     return keep ? fmaf(y, om, -diff) * inv : 0.f;
 }
 
+// the same for the two packed voxels of a lane pair (f32x2 arithmetic; SFU operations and the table rows per lane).
+// ys = observed magnitude with the mask in its sign bit (negative = masked).
+__device__ __forceinline__ pk rician_echo(const float4 *__restrict__ btab, float te, pk a2, pk ys, pk nu_unmasked, pk s_phi, pk mu, pk s_r, bool rem,
+                                          UqAcc2 &acc) {
+    const float k = kTwoPi * te, k2 = k * k;
+    const pk x = vmul(k2, s_phi);
+    const pk ephi = fast_ex2(vmul(-kLog2e, x));
+    pk s = vfma(x, splat<pk>(-1.0f / 5040.0f), splat<pk>(1.0f / 720.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 120.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 24.0f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f / 6.0f));
+    s = vfma(vneg(x), s, splat<pk>(0.5f));
+    s = vfma(vneg(x), s, splat<pk>(1.0f));
+    const pk series = vmul(x, s), direct = vsub(splat<pk>(1.0f), ephi);
+    const pk vphi = mk(x.d.x < 0.25f ? series.d.x : direct.d.x, x.d.y < 0.25f ? series.d.y : direct.d.y);
+    pk er = splat<pk>(0.f);
+    if (!rem) er = vmul(te * te, fast_ex2(vmul(-te * kLog2e, mu)));
+    const pk var = vmul(vfma(er, s_r, vphi), a2);
+    const bool g0 = var.d.x >= kVarFloor, g1 = var.d.y >= kVarFloor;
+    const pk s2 = mk(g0 ? var.d.x : kVarFloor, g1 ? var.d.y : kVarFloor);
+    const pk inv = mk(rcp_ftz(s2.d.x), rcp_ftz(s2.d.y));
+    const bool k0 = !signbit(ys.d.x), k1 = !signbit(ys.d.y);
+    const pk y = mk(fabsf(ys.d.x), fabsf(ys.d.y));
+    const pk nu = mk(k0 ? nu_unmasked.d.x : 0.f, k1 ? nu_unmasked.d.y : 0.f);
+    const pk ynu = vmul(y, nu), z = vmul(ynu, inv);
+    pk li0e, om;
+    bessel_terms(btab, z.d.x, li0e.d.x, om.d.x);
+    bessel_terms(btab, z.d.y, li0e.d.y, om.d.y);
+    const pk diff = vsub(y, nu);
+    const pk hd = vmul(vmul(0.5f, diff), diff);
+    const pk ratio = mk(y.d.x > 1e-5f ? s2.d.x * rcp_ftz(y.d.x) : s2.d.x, y.d.y > 1e-5f ? s2.d.y * rcp_ftz(y.d.y) : s2.d.y);
+    const pk lg = mk(lg2_ftz(ratio.d.x), lg2_ftz(ratio.d.y));
+    acc.loss = vadd(acc.loss, vfma(hd, inv, vfma(splat<pk>(kLn2), lg, vneg(li0e))));
+    pk gv = vmul(inv, vfma(vneg(vfma(ynu, om, hd)), inv, splat<pk>(1.0f)));
+    gv = mk(g0 ? gv.d.x : 0.f, g1 ? gv.d.y : 0.f);
+    const pk ga = vmul(gv, a2);
+    acc.g_sphi = vfma(vmul(k2, ga), ephi, acc.g_sphi);
+    acc.g_mu = vfma(vmul(-te, ga), vmul(er, s_r), acc.g_mu);
+    acc.g_sr = vfma(ga, er, acc.g_sr);
+    const pk g = vmul(vfma(y, om, vneg(diff)), inv);
+    return mk(k0 ? g.d.x : 0.f, k1 ? g.d.y : 0.f);
+}
+
 // host: the same objective on the TMA ring of ig_solve.cu (IG_E_UNSUPPORTED when the shape is not covered)
 int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
                      const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
