@@ -25,6 +25,23 @@ __device__ __forceinline__ float one_minus_exp_neg(float x, float &e) {
     return 1.0f - e;
 }
 
+// SFU approximations without the denormal-range wrappers of rsqrtf / __logf / __fdividef (arguments here are >= 1e-5)
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // per-echo uncertainty terms of one voxel: variance, its floor gate, 1/std, and the accumulation of the moment gradients
 struct UqAcc {
     float g_sphi, g_mu, g_sr, loss;
@@ -37,7 +54,7 @@ __device__ __forceinline__ float uq_echo(float te, float a2, float msd, float s_
     const float var = fmaf(er, s_r, vphi) * a2;
     const bool gate = var >= kVarFloor;
     const float varc = gate ? var : kVarFloor;
-    const float inv_std = rsqrtf(varc);
+    const float inv_std = rsqrt_ftz(varc);
     float lg;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(varc));
     acc.loss += fmaf(msd, inv_std, lg * kLn2);
@@ -71,7 +88,7 @@ __device__ __forceinline__ pk uq_echo(float te, pk a2, pk msd, pk s_phi, pk mu, 
     const pk var = vmul(vfma(er, s_r, vphi), a2);
     const bool g0 = var.d.x >= kVarFloor, g1 = var.d.y >= kVarFloor;
     const pk varc = mk(g0 ? var.d.x : kVarFloor, g1 ? var.d.y : kVarFloor);
-    const pk inv_std = mk(rsqrtf(varc.d.x), rsqrtf(varc.d.y));
+    const pk inv_std = mk(rsqrt_ftz(varc.d.x), rsqrt_ftz(varc.d.y));
     float l0, l1;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(varc.d.x));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(varc.d.y));
@@ -144,22 +161,6 @@ constexpr int kBesselRows = 136, kBesselRowBase = 468;          // rows for 2^-1
 __device__ __align__(16) const float kBesselTab[kBesselRows * 12] = {
 #include "ig_bessel_tab.inc"
 };
-
-__device__ __forceinline__ float lg2_ftz(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 // cooperative copy of the table into shared memory (16-byte rows of a float4 array); caller synchronises
 __device__ __forceinline__ void stage_bessel_table(float4 *smem_tab) {
