@@ -223,7 +223,11 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     g_pm = torch.empty((NB, 1, H, W, 2), dtype=torch.float32, device=device)
     from idealgan import dist as igdist
-    reducer = igdist.AsyncLossReducer(device, depth=2)          # the scalar all-reduce of step i overlaps the kernels of step i + 1
+    # the scalar exchange: "peer" = fused into the loss kernel (stores into every rank's mailbox over NVLink, no collective
+    # kernel); "nccl" = asynchronous all-reduce of step i under the kernels of step i + 1
+    peer = igdist.PeerLossExchange(device) if (world > 1 and args.exchange == "peer") else None
+    reducer = igdist.AsyncLossReducer(device, depth=2)
+    loss_local = torch.zeros(1, dtype=torch.float32, device=device)
     scratch = ops.loss_scratch(device, NB, nv)
     te2 = te[:, :, 0].contiguous()
     # The per-sample tables depend on the echo times only, which arrive with the batch, ahead of the maps: every step builds
@@ -245,13 +249,20 @@ def run_ours(args):
         stream.wait_event(tab_ready[j])
         if ev:
             ev[0].record(stream)
-        L.check(lib.ig_a2a_loss(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
-                                loss.data_ptr(), scratch.data_ptr(), scratch.numel(), stream.cuda_stream), "ig_a2a_loss")
+        if peer is not None:
+            L.check(lib.ig_a2a_loss_peer(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
+                                         loss_local.data_ptr(), scratch.data_ptr(), scratch.numel(), peer.handle, peer.step, peer.prev.data_ptr(),
+                                         stream.cuda_stream), "ig_a2a_loss_peer")
+            peer.step += 1
+        else:
+            L.check(lib.ig_a2a_loss(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
+                                    loss.data_ptr(), scratch.data_ptr(), scratch.numel(), stream.cuda_stream), "ig_a2a_loss")
         if ev:
             ev[1].record(stream)
         tab_free[j] = torch.cuda.Event()
         tab_free[j].record(stream)
-        reducer.submit()                                  # scalar loss over NVLink: the only exchange on this path
+        if peer is None:
+            reducer.submit()                              # scalar loss over NVLink: the only exchange on this path
 
     def fence():
         if dist is not None:
@@ -269,12 +280,14 @@ def run_ours(args):
         side.wait_event(t0)                               # no table of a timed step starts before the opening event
         for i in range(args.steps):
             step(kev[i])
+        if peer is not None:
+            peer.last(stream.cuda_stream)                 # the last step's global scalar is complete before the closing event
         reducer.drain()                                   # every reduction is ordered before the closing event
         t1.record(stream)
         fence()
     ms = t0.elapsed_time(t1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    final_loss = reducer.last().item()
+    final_loss = (peer._last if peer is not None else reducer.last()).item()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------------------
     e2e_s, e2e_steps, e2e_loss, h2d, d2h = 0.0, 0, None, 0, 0
@@ -353,9 +366,10 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": NB * world, "sharding": f"batch axis, {NB} slices per GPU, "
-                       "async NCCL all-reduce of the scalar loss only (overlaps the next step)" if world > 1 else "single GPU",
+                       + ("scalar loss exchanged by the loss kernel itself (peer-memory stores over NVLink, no collective kernel)" if peer is not None
+                          else "async NCCL all-reduce of the scalar loss only (overlaps the next step)") if world > 1 else "single GPU",
                        "l2": f"inputs {(acqs.numel() + pm.numel()) * 4 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
-                       "step": "ig_gen_tables (side stream, double-buffered) + ig_a2a_loss (fused loss + gradient)" + (" + async all_reduce(loss)" if world > 1 else ""),
+                       "step": "ig_gen_tables (side stream, double-buffered) + ig_a2a_loss (fused loss + gradient)" + ((" with the scalar exchange fused in (ig_a2a_loss_peer)" if peer is not None else " + async all_reduce(loss)") if world > 1 else ""),
                        "loss": final_loss, "e2e_loss": e2e_loss},
             "clocks": clocks.summary(),
             "e2e": None if not e2e_steps else {
@@ -384,6 +398,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--chunk", type=int, default=8, help="slices per chunk of the host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer", help="multi-GPU scalar exchange (see idealgan/dist.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (profiling runs)")
     args = ap.parse_args()

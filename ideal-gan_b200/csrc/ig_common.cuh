@@ -273,7 +273,53 @@ template <typename V> __device__ __forceinline__ cx<V> demod_fwd(const Mod<V> &m
 // ------------------------------------------------------------------------------------------------
 constexpr size_t kScratchHeader = 16;
 
-__device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float *loss_out, float scale) {
+// Scalar exchange between the GPUs of a data-parallel job, fused into the objective's finishing block (ig_peer.cu): every
+// rank owns a mailbox of kPeerSlots x world 8-byte words {step + 1, float bits}; the finishing thread of step i stores its
+// scalar into slot i % kPeerSlots of EVERY rank's mailbox (its own through a local pointer, the others through IPC-mapped
+// peer memory: posted stores over NVLink, nothing waits for them) and then adds up the `world` words of step i - 1 in its own
+// mailbox in rank order (identical bits on every rank).  No collective kernel, no host call.  boxes == nullptr: off.
+constexpr int kPeerSlots = 4;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;       // a peer that never delivers gives NaN, not a hung GPU
+struct PeerPub {
+    unsigned long long *const *boxes;      // device array [world] of mailbox base pointers
+    float *prev_out;                       // <- global scalar of step - 1 (optional)
+    int rank, world;
+    unsigned step;
+};
+
+int peer_pub(const ig_peer *peer, unsigned step, float *prev_out, PeerPub *out);      // ig_peer.cu: fills the kernel-side view
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// sum over ranks of the words of `step` in `box` (fp64, rank order); NaN after kPeerTimeoutNs
+__device__ __forceinline__ float peer_collect(const unsigned long long *box, int world, unsigned step) {
+    const volatile unsigned long long *slot = box + static_cast<size_t>(step % kPeerSlots) * world;
+    const unsigned long long t0 = global_timer_ns();
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) {
+        unsigned long long w = slot[r];
+        while (static_cast<unsigned>(w >> 32) != step + 1u) {
+            if (global_timer_ns() - t0 > kPeerTimeoutNs) return __int_as_float(0x7fc00000);
+            __nanosleep(64);
+            w = slot[r];
+        }
+        acc += static_cast<double>(__uint_as_float(static_cast<unsigned>(w)));
+    }
+    return static_cast<float>(acc);
+}
+
+__device__ __forceinline__ void peer_exchange(const PeerPub &peer, float value) {
+    const unsigned long long word = (static_cast<unsigned long long>(peer.step + 1u) << 32) | __float_as_uint(value);
+    const size_t at = static_cast<size_t>(peer.step % kPeerSlots) * peer.world + peer.rank;
+    for (int r = 0; r < peer.world; ++r) *reinterpret_cast<volatile unsigned long long *>(peer.boxes[r] + at) = word;
+    if (peer.prev_out && peer.step > 0) peer.prev_out[0] = peer_collect(peer.boxes[peer.rank], peer.world, peer.step - 1u);
+}
+
+__device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float *loss_out, float scale, const PeerPub peer = PeerPub{}) {
     __shared__ float warp_part[32];
     __shared__ bool is_last;
 #pragma unroll
@@ -305,9 +351,11 @@ __device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float 
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < nwarp; ++w) s += dpart[w];
-        loss_out[0] = static_cast<float>(s * static_cast<double>(scale));
+        const float total = static_cast<float>(s * static_cast<double>(scale));
+        loss_out[0] = total;
         ticket[0] = 0u;
         ticket[1] = 0u;      // dynamic tile counter of the persistent kernels
+        if (peer.boxes) peer_exchange(peer, total);
     }
 }
 

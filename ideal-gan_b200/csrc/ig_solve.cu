@@ -29,6 +29,7 @@ struct SolveParams {
     int nb, ne, nv, flags;
     int tile_stride;      // persistent kernels: visit a sample's tiles in the order (j * tile_stride) % tiles_per_sample
     float r2_sc, inv_n;
+    PeerPub peer;         // a2a objective only: scalar exchange with the other ranks in the finishing block (off when boxes == nullptr)
 };
 
 // echo loads / stores for both acquisition layouts
@@ -585,7 +586,7 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
         }
     }
     }   // tile loop
-    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n, p.peer);
 }
 
 // =================================================================================================
@@ -1043,7 +1044,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
             if (lane == 0) mbar_arrive(&empty_bar[s]);                        // this warp no longer touches the stage
         }
     }
-    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n);
+    block_loss_reduce(loss_part, p.scratch, p.loss, p.inv_n, p.peer);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1311,16 +1312,16 @@ extern "C" int ig_a2a_bwd(const float *acqs_d, const float *pm_d, long pm_bstrid
     });
 }
 
-extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
-                           float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
-                           size_t scratch_bytes, void *stream) {
+static int a2a_loss_impl(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv, float r2_sc, float inv_n,
+                         float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d, size_t scratch_bytes, void *stream,
+                         const PeerPub &peer) {
     IG_REQUIRE(acqs_d && pm_d && tab_d && g_pm_d && loss_d && scratch_d, IG_E_ARG, "ig_a2a_loss: null pointer");
     if (int rc = check_common("ig_a2a_loss", nb, ne, nv, 2)) return rc;
     IG_REQUIRE(scratch_bytes >= ig_loss_scratch_bytes(nb, nv), IG_E_SCRATCH, "ig_a2a_loss: scratch %zu < %zu bytes", scratch_bytes,
                ig_loss_scratch_bytes(nb, nv));
     SolveParams p{};
     p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.tab = tab_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
-    p.inv_n = inv_n; p.g_pm = g_pm_d; p.rho = rho_d; p.shat = shat_d; p.loss = loss_d; p.scratch = scratch_d;
+    p.inv_n = inv_n; p.g_pm = g_pm_d; p.rho = rho_d; p.shat = shat_d; p.loss = loss_d; p.scratch = scratch_d; p.peer = peer;
     const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, g_pm_d, rho_d, shat_d});
     const bool outputs = rho_d || shat_d;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1338,4 +1339,20 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
         }
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
+}
+
+extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                           float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
+                           size_t scratch_bytes, void *stream) {
+    return a2a_loss_impl(acqs_d, pm_d, pm_bstride, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d, rho_d, shat_d, loss_d, scratch_d, scratch_bytes, stream,
+                         PeerPub{});
+}
+
+extern "C" int ig_a2a_loss_peer(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                                float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
+                                size_t scratch_bytes, ig_peer *peer, unsigned step, float *loss_prev_d, void *stream) {
+    IG_REQUIRE(peer, IG_E_ARG, "ig_a2a_loss_peer: null peer context");
+    PeerPub pub{};
+    if (int rc = peer_pub(peer, step, loss_prev_d, &pub)) return rc;
+    return a2a_loss_impl(acqs_d, pm_d, pm_bstride, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d, rho_d, shat_d, loss_d, scratch_d, scratch_bytes, stream, pub);
 }

@@ -27,6 +27,7 @@ def unpack_table(tab, ne):
             "pw": (rec[:, :, REC_PW_RE], rec[:, :, REC_PW_IM]), "pf": (rec[:, :, REC_PF_RE], rec[:, :, REC_PF_IM]),
             "ap": ap, "rec": rec}
 MODEL_WFPM, MODEL_FFPD, MODEL_MAGPHA = 0, 1, 2
+PEER_HANDLE_BYTES = 64
 F_PHASE_CONSTRAINT, F_FLAT, F_ONLY_MAG, F_NO_RELU = 1, 2, 4, 8
 
 _fp = C.c_void_p          # device / host float pointers travel as integers
@@ -66,6 +67,13 @@ SIGNATURES = {
     "ig_acq_from_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
     "ig_maps_to_flat": (_i, [_fp, _i, _i, _i, _i, _f, _fp, _fp]),
     "ig_maps_from_flat": (_i, [_fp, _i, _i, _i, _fp, _fp]),
+    "ig_peer_create": (_i, [_i, _i, C.POINTER(C.c_void_p)]),
+    "ig_peer_handle": (_i, [C.c_void_p, _fp]),
+    "ig_peer_connect": (_i, [C.c_void_p, _fp]),
+    "ig_peer_connect_local": (_i, [C.POINTER(C.c_void_p), _i]),
+    "ig_a2a_loss_peer": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, C.c_void_p, C.c_uint, _fp, _fp]),
+    "ig_peer_reduce": (_i, [C.c_void_p, C.c_uint, _fp, _fp]),
+    "ig_peer_destroy": (None, [C.c_void_p]),
     "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),
     "ig_ctx_destroy": (None, [C.c_void_p]),
     "ig_a2a_loss_host": (_i, [C.c_void_p, _fp, _fp, _fp, _i, _f, _f, _f, _fp, _fp]),

@@ -101,6 +101,83 @@ class AsyncLossReducer:
         return self.bufs[self.step % len(self.bufs)]
 
 
+class PeerLossExchange:
+    """The objective's scalar exchange without a collective: every rank's loss kernel stores its scalar straight into every
+    rank's mailbox over NVLink (CUDA-IPC-mapped peer memory) from its finishing thread, and sums the previous step's
+    scalars, which have arrived by then (ig_a2a_loss_peer, include/idealgan.h).  No NCCL kernel competes with the
+    objective's persistent blocks for SMs, and the host issues one launch per step instead of two.
+
+        ex = PeerLossExchange(device)                 # collective over the default group: exchanges the IPC handles once
+        for i in ...:
+            loss_local, g_pm = ex.a2a_loss(acqs, pm, tab, inv_n=...)      # ex.prev: global loss of step i - 1 (device scalar)
+        ex.last()                                     # global loss of the most recent step
+
+    torch.distributed is used once, for the 64-byte handles (any backend); a single process (world 1) needs none."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        from . import _lib as L
+        self._L, self._ct = L, ctypes
+        self.device = torch.device(device)
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.step = 0
+        self.prev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._last = torch.zeros(1, dtype=torch.float32, device=self.device)
+        lib = L.load()
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(lib.ig_peer_create(self.rank, self.world, ctypes.byref(self.handle)), "ig_peer_create")
+            if self.world > 1:
+                mine = (ctypes.c_ubyte * L.PEER_HANDLE_BYTES)()
+                L.check(lib.ig_peer_handle(self.handle, ctypes.addressof(mine)), "ig_peer_handle")
+                t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
+                parts = [torch.empty_like(t) for _ in range(self.world)]
+                dist.all_gather(parts, t, group=group)
+                blob = bytes(torch.cat(parts).cpu().numpy().tobytes())
+                buf = ctypes.create_string_buffer(blob, len(blob))
+                L.check(lib.ig_peer_connect(self.handle, ctypes.addressof(buf)), "ig_peer_connect")
+                dist.barrier(group=group)          # every mailbox is mapped everywhere before the first store
+
+    def a2a_loss(self, acqs, pm, tab, r2_sc=200.0, inv_n=None, g_pm=None, loss=None, scratch=None, stream=None):
+        """ops.a2a_loss with the exchange fused in.  Returns (local loss (1,), g_pm); self.prev receives the global loss of the
+        previous step."""
+        from . import ops
+        L = self._L
+        nb, ne, H, W, _ = acqs.shape
+        nv = H * W
+        inv_n = 1.0 / (acqs.numel() * self.world) if inv_n is None else float(inv_n)
+        g_pm = torch.empty((nb, 1, H, W, 2), dtype=torch.float32, device=acqs.device) if g_pm is None else g_pm
+        loss = torch.empty(1, dtype=torch.float32, device=acqs.device) if loss is None else loss
+        scratch = ops.loss_scratch(acqs.device, nb, nv) if scratch is None else scratch
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        L.check(L.load().ig_a2a_loss_peer(acqs.data_ptr(), pm.data_ptr(), pm.stride(0), tab.data_ptr(), nb, ne, nv, float(r2_sc), inv_n,
+                                          g_pm.data_ptr(), 0, 0, loss.data_ptr(), scratch.data_ptr(), scratch.numel(), self.handle, self.step,
+                                          self.prev.data_ptr(), st), "ig_a2a_loss_peer")
+        self.step += 1
+        return loss, g_pm
+
+    def last(self, stream=None):
+        """Global loss of the most recent step (launches the one-warp reduction; waits for the peers on the device)."""
+        if self.step == 0:
+            raise RuntimeError("last() before the first step")
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._L.check(self._L.load().ig_peer_reduce(self.handle, self.step - 1, self._last.data_ptr(), st), "ig_peer_reduce")
+        return self._last
+
+    def close(self):
+        if self.handle:
+            self._L.load().ig_peer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def synthesize_to_host(model, maps_host, te, out_host=None, field=1.5, r2_sc=200.0, chunk_nb=256, flags=0, device=None):
     """Physics decoding of a shard that does not fit (or is not wanted) on the device in one piece -- config 5, the PI-VAE / LDM
     dataset synthesis of gen_LDM_dataset.py:140-254, whose 16 384 x 384 x 384 x 6 echoes are 116 GB.  `maps_host` (pinned CPU

@@ -203,6 +203,31 @@ int ig_maps_to_flat(const float *maps_d, int nb, int nv, int mode, int ch, float
  * 3 'PM' (nb,nv,2) -> (nb,1,nv,2). */
 int ig_maps_from_flat(const float *flat_d, int nb, int nv, int mode, float *maps_d, void *stream);
 
+/* ---- multi-GPU: scalar-loss exchange over peer memory, fused into the objective's kernel ---- */
+/* One process per GPU.  Each rank owns a small device mailbox; the finishing thread of the objective's kernel stores the
+ * rank's scalar into every rank's mailbox (own: local pointer, others: CUDA-IPC-mapped peer memory, i.e. posted stores over
+ * NVLink) and adds up the scalars of the PREVIOUS step, which have arrived by then: no collective kernel, no host call, no
+ * extra launch.  Replaces the `all_reduce` a data-parallel run of train-IDEAL-unsup.py would issue for its logged loss.
+ *   ig_peer_create   on the current device; rank in [0, world), world <= 64
+ *   ig_peer_handle   -> 64 opaque bytes (a cudaIpcMemHandle_t) to hand to the other ranks (any transport)
+ *   ig_peer_connect  handles of ALL ranks in rank order (world x 64 bytes); own entry is ignored
+ *   ig_peer_connect_local  same-process alternative (threads / tests): the contexts of all ranks, in rank order
+ *   ig_a2a_loss_peer = ig_a2a_loss + publication of step `step`'s scalar; loss_prev_d (optional) <- global loss of step - 1.
+ *                      `step` must increase by 1 per call on every rank (mailbox slots rotate; ranks stay within one step).
+ *   ig_peer_reduce   global loss of `step` into loss_d (tiny kernel; for the last step, or whenever the scalar is needed at once)
+ * A rank that never delivers yields NaN after 2 s instead of a hung GPU. */
+typedef struct ig_peer ig_peer;
+#define IG_PEER_HANDLE_BYTES 64
+int ig_peer_create(int rank, int world, ig_peer **out);
+int ig_peer_handle(ig_peer *peer, void *handle_out);
+int ig_peer_connect(ig_peer *peer, const void *handles);
+int ig_peer_connect_local(ig_peer *const *peers, int world);
+int ig_a2a_loss_peer(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
+                     float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
+                     size_t scratch_bytes, ig_peer *peer, unsigned step, float *loss_prev_d, void *stream);
+int ig_peer_reduce(ig_peer *peer, unsigned step, float *loss_d, void *stream);
+void ig_peer_destroy(ig_peer *peer);
+
 /* ---- host-buffer pipeline (the call timed as `e2e` by bench.py) -------------------------------- */
 /* A context owns device staging buffers and streams on `device`; chunks of `chunk_nb` samples are copied
  * host->device, processed and copied back with copy/compute overlap.  Host buffers should be pinned. */
