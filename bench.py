@@ -225,7 +225,13 @@ def run_ours(args):
     from idealgan import dist as igdist
     # the scalar exchange: "peer" = fused into the loss kernel (stores into every rank's mailbox over NVLink, no collective
     # kernel); "nccl" = asynchronous all-reduce of step i under the kernels of step i + 1
-    peer = igdist.PeerLossExchange(device) if (world > 1 and args.exchange == "peer") else None
+    peer, exchange_note = None, None
+    if world > 1 and args.exchange == "peer":
+        try:
+            peer = igdist.PeerLossExchange(device)       # collective set-up: fails on every rank or on none
+        except RuntimeError as e:
+            exchange_note = f"peer exchange unavailable ({e}); NCCL all-reduce used"
+            print(exchange_note, file=sys.stderr)
     reducer = igdist.AsyncLossReducer(device, depth=2)
     loss_local = torch.zeros(1, dtype=torch.float32, device=device)
     scratch = ops.loss_scratch(device, NB, nv)
@@ -370,7 +376,7 @@ def run_ours(args):
                           else "async NCCL all-reduce of the scalar loss only (overlaps the next step)") if world > 1 else "single GPU",
                        "l2": f"inputs {(acqs.numel() + pm.numel()) * 4 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
                        "step": "ig_gen_tables (side stream, double-buffered) + ig_a2a_loss (fused loss + gradient)" + ((" with the scalar exchange fused in (ig_a2a_loss_peer)" if peer is not None else " + async all_reduce(loss)") if world > 1 else ""),
-                       "loss": final_loss, "e2e_loss": e2e_loss},
+                       "loss": final_loss, "e2e_loss": e2e_loss, **({"exchange_note": exchange_note} if exchange_note else {})},
             "clocks": clocks.summary(),
             "e2e": None if not e2e_steps else {
                     "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -123,22 +123,44 @@ class PeerLossExchange:
         self.rank = dist.get_rank(group) if on else 0
         self.world = dist.get_world_size(group) if on else 1
         self.step = 0
-        self.prev = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self._last = torch.zeros(1, dtype=torch.float32, device=self.device)
         lib = L.load()
         self.handle = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            L.check(lib.ig_peer_create(self.rank, self.world, ctypes.byref(self.handle)), "ig_peer_create")
-            if self.world > 1:
-                mine = (ctypes.c_ubyte * L.PEER_HANDLE_BYTES)()
-                L.check(lib.ig_peer_handle(self.handle, ctypes.addressof(mine)), "ig_peer_handle")
-                t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
-                parts = [torch.empty_like(t) for _ in range(self.world)]
-                dist.all_gather(parts, t, group=group)
-                blob = bytes(torch.cat(parts).cpu().numpy().tobytes())
+        # Set-up is collective and must not strand the other ranks when one of them fails (no IPC in a container, no peer
+        # access): every rank always takes part in the handle all-gather and in the final status reduction, and all raise together.
+        err = None
+        mine = (ctypes.c_ubyte * L.PEER_HANDLE_BYTES)()
+        try:
+            with torch.cuda.device(self.device):
+                L.check(lib.ig_peer_create(self.rank, self.world, ctypes.byref(self.handle)), "ig_peer_create")
+                if self.world > 1:
+                    L.check(lib.ig_peer_handle(self.handle, ctypes.addressof(mine)), "ig_peer_handle")
+        except Exception as e:      # noqa: BLE001
+            err = e
+        if self.world > 1:
+            on_dev = dist.get_backend(group) == "nccl"
+            t = torch.tensor(list(mine) + [0 if err is None else 1], dtype=torch.uint8, device=self.device if on_dev else "cpu")
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t, group=group)
+            parts = [p.cpu() for p in parts]
+            if err is None and not any(int(p[-1]) for p in parts):
+                blob = b"".join(bytes(p[:-1].numpy().tobytes()) for p in parts)
                 buf = ctypes.create_string_buffer(blob, len(blob))
-                L.check(lib.ig_peer_connect(self.handle, ctypes.addressof(buf)), "ig_peer_connect")
-                dist.barrier(group=group)          # every mailbox is mapped everywhere before the first store
+                try:
+                    with torch.cuda.device(self.device):
+                        L.check(lib.ig_peer_connect(self.handle, ctypes.addressof(buf)), "ig_peer_connect")
+                except Exception as e:      # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("peer exchange: another rank failed to create its mailbox")
+            bad = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device if on_dev else "cpu")
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)      # also the barrier: every mailbox is mapped everywhere
+            if int(bad.item()) and err is None:
+                err = RuntimeError("peer exchange: another rank failed to map the mailboxes")
+        if err is not None:
+            self.close()
+            raise RuntimeError(f"PeerLossExchange set-up failed on rank {self.rank}: {err}")
+        self.prev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._last = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def a2a_loss(self, acqs, pm, tab, r2_sc=200.0, inv_n=None, g_pm=None, loss=None, scratch=None, stream=None):
         """ops.a2a_loss with the exchange fused in.  Returns (local loss (1,), g_pm); self.prev receives the global loss of the

@@ -111,3 +111,30 @@ def test_async_loss_reducer_single_process_is_a_no_op():
         red.acquire().fill_(step + 1.0)
         red.submit()
     assert red.last().item() == 4.0
+
+
+def _peer_setup_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            igdist.PeerLossExchange(torch.device("cuda", 0))      # no CUDA device here: mailbox creation fails
+            out[rank] = "created"
+        except RuntimeError as e:
+            out[rank] = str(e)
+        dist.barrier()                                             # nobody was left behind in a collective
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="failure path: needs a box without a GPU")
+def test_peer_exchange_setup_fails_on_every_rank_together():
+    """PeerLossExchange's set-up is collective: when the mailbox cannot be created (no GPU here) every rank raises, none hangs."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_peer_setup_worker, args=(world, port, out), nprocs=world, join=True)
+        assert len(out) == world
+        for r in range(world):
+            assert "set-up failed" in out[r], out[r]
