@@ -228,7 +228,7 @@ def run_ours(args):
     peer, exchange_note = None, None
     if world > 1 and args.exchange == "peer":
         try:
-            peer = igdist.PeerLossExchange(device)       # collective set-up: fails on every rank or on none
+            peer = igdist.PeerLossExchange(device, lag=args.lag)       # collective set-up: fails on every rank or on none
         except RuntimeError as e:
             exchange_note = f"peer exchange unavailable ({e}); NCCL all-reduce used"
             print(exchange_note, file=sys.stderr)
@@ -257,7 +257,7 @@ def run_ours(args):
             ev[0].record(stream)
         if peer is not None:
             L.check(lib.ig_a2a_loss_peer(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
-                                         loss_local.data_ptr(), scratch.data_ptr(), scratch.numel(), peer.handle, peer.step, peer.prev.data_ptr(),
+                                         loss_local.data_ptr(), scratch.data_ptr(), scratch.numel(), peer.handle, peer.step, peer.lag, peer.prev.data_ptr(),
                                          stream.cuda_stream), "ig_a2a_loss_peer")
             peer.step += 1
         else:
@@ -405,6 +405,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="slices per chunk of the host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer", help="multi-GPU scalar exchange (see idealgan/dist.py)")
+    ap.add_argument("--lag", type=int, default=1, help="peer exchange: the global loss a step receives is `lag` steps old")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (profiling runs)")
     args = ap.parse_args()

@@ -276,18 +276,22 @@ constexpr size_t kScratchHeader = 16;
 // Scalar exchange between the GPUs of a data-parallel job, fused into the objective's finishing block (ig_peer.cu): every
 // rank owns a mailbox of kPeerSlots x world 8-byte words {step + 1, float bits}; the finishing thread of step i stores its
 // scalar into slot i % kPeerSlots of EVERY rank's mailbox (its own through a local pointer, the others through IPC-mapped
-// peer memory: posted stores over NVLink, nothing waits for them) and then adds up the `world` words of step i - 1 in its own
-// mailbox in rank order (identical bits on every rank).  No collective kernel, no host call.  boxes == nullptr: off.
-constexpr int kPeerSlots = 4;
+// peer memory: posted stores over NVLink, nothing waits for them) and then adds up the `world` words of step i - lag in its
+// own mailbox in rank order (identical bits on every rank).  No collective kernel, no host call.  boxes == nullptr: off.
+// lag = 1 makes every step wait for the slowest rank's previous step; lag = 2 leaves a step of slack, so the wait is only
+// taken when a rank really falls behind.  A rank publishes step j + 1 having seen its peers' step j - lag, whose readers may
+// still be on step j - 2 lag: slots must outnumber 2 lag + 1.
+constexpr int kPeerSlots = 8;
+constexpr int kPeerMaxLag = 3;
 constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;       // a peer that never delivers gives NaN, not a hung GPU
 struct PeerPub {
     unsigned long long *const *boxes;      // device array [world] of mailbox base pointers
-    float *prev_out;                       // <- global scalar of step - 1 (optional)
+    float *prev_out;                       // <- global scalar of step - lag (optional)
     int rank, world;
-    unsigned step;
+    unsigned step, lag;
 };
 
-int peer_pub(const ig_peer *peer, unsigned step, float *prev_out, PeerPub *out);      // ig_peer.cu: fills the kernel-side view
+int peer_pub(const ig_peer *peer, unsigned step, int lag, float *prev_out, PeerPub *out);      // ig_peer.cu: fills the kernel-side view
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
@@ -316,7 +320,7 @@ __device__ __forceinline__ void peer_exchange(const PeerPub &peer, float value) 
     const unsigned long long word = (static_cast<unsigned long long>(peer.step + 1u) << 32) | __float_as_uint(value);
     const size_t at = static_cast<size_t>(peer.step % kPeerSlots) * peer.world + peer.rank;
     for (int r = 0; r < peer.world; ++r) *reinterpret_cast<volatile unsigned long long *>(peer.boxes[r] + at) = word;
-    if (peer.prev_out && peer.step > 0) peer.prev_out[0] = peer_collect(peer.boxes[peer.rank], peer.world, peer.step - 1u);
+    if (peer.prev_out && peer.step >= peer.lag) peer.prev_out[0] = peer_collect(peer.boxes[peer.rank], peer.world, peer.step - peer.lag);
 }
 
 __device__ __forceinline__ void block_loss_reduce(float v, void *scratch, float *loss_out, float scale, const PeerPub peer = PeerPub{}) {

@@ -17,13 +17,15 @@ struct ig_peer {
 
 namespace ig {
 
-int peer_pub(const ig_peer *peer, unsigned step, float *prev_out, PeerPub *out) {
+int peer_pub(const ig_peer *peer, unsigned step, int lag, float *prev_out, PeerPub *out) {
     IG_REQUIRE(peer->connected, IG_E_ARG, "ig_peer: not connected (ig_peer_connect / ig_peer_connect_local first)");
+    IG_REQUIRE(lag >= 1 && lag <= kPeerMaxLag, IG_E_ARG, "ig_peer: lag %d outside [1, %d]", lag, kPeerMaxLag);
     out->boxes = peer->boxes_d;
     out->prev_out = prev_out;
     out->rank = peer->rank;
     out->world = peer->world;
     out->step = step;
+    out->lag = static_cast<unsigned>(lag);
     return 0;
 }
 

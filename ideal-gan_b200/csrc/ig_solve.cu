@@ -1350,9 +1350,9 @@ extern "C" int ig_a2a_loss(const float *acqs_d, const float *pm_d, long pm_bstri
 
 extern "C" int ig_a2a_loss_peer(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
                                 float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
-                                size_t scratch_bytes, ig_peer *peer, unsigned step, float *loss_prev_d, void *stream) {
+                                size_t scratch_bytes, ig_peer *peer, unsigned step, int lag, float *loss_prev_d, void *stream) {
     IG_REQUIRE(peer, IG_E_ARG, "ig_a2a_loss_peer: null peer context");
     PeerPub pub{};
-    if (int rc = peer_pub(peer, step, loss_prev_d, &pub)) return rc;
+    if (int rc = peer_pub(peer, step, lag, loss_prev_d, &pub)) return rc;
     return a2a_loss_impl(acqs_d, pm_d, pm_bstride, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d, rho_d, shat_d, loss_d, scratch_d, scratch_bytes, stream, pub);
 }

@@ -109,15 +109,18 @@ class PeerLossExchange:
 
         ex = PeerLossExchange(device)                 # collective over the default group: exchanges the IPC handles once
         for i in ...:
-            loss_local, g_pm = ex.a2a_loss(acqs, pm, tab, inv_n=...)      # ex.prev: global loss of step i - 1 (device scalar)
+            loss_local, g_pm = ex.a2a_loss(acqs, pm, tab, inv_n=...)      # ex.prev: global loss of step i - lag (device scalar)
         ex.last()                                     # global loss of the most recent step
 
     torch.distributed is used once, for the 64-byte handles (any backend); a single process (world 1) needs none."""
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, lag=1):
         import ctypes
         from . import _lib as L
         self._L, self._ct = L, ctypes
+        if lag not in (1, 2, 3):
+            raise ValueError("lag must be 1, 2 or 3")
+        self.lag = lag
         self.device = torch.device(device)
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if on else 0
@@ -164,7 +167,7 @@ class PeerLossExchange:
 
     def a2a_loss(self, acqs, pm, tab, r2_sc=200.0, inv_n=None, g_pm=None, loss=None, scratch=None, stream=None):
         """ops.a2a_loss with the exchange fused in.  Returns (local loss (1,), g_pm); self.prev receives the global loss of the
-        previous step."""
+        step `lag` steps back (lag 2: no rank ever waits for a peer that is less than a step behind)."""
         from . import ops
         L = self._L
         nb, ne, H, W, _ = acqs.shape
@@ -176,7 +179,7 @@ class PeerLossExchange:
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         L.check(L.load().ig_a2a_loss_peer(acqs.data_ptr(), pm.data_ptr(), pm.stride(0), tab.data_ptr(), nb, ne, nv, float(r2_sc), inv_n,
                                           g_pm.data_ptr(), 0, 0, loss.data_ptr(), scratch.data_ptr(), scratch.numel(), self.handle, self.step,
-                                          self.prev.data_ptr(), st), "ig_a2a_loss_peer")
+                                          self.lag, self.prev.data_ptr(), st), "ig_a2a_loss_peer")
         self.step += 1
         return loss, g_pm
 

@@ -212,8 +212,9 @@ int ig_maps_from_flat(const float *flat_d, int nb, int nv, int mode, float *maps
  *   ig_peer_handle   -> 64 opaque bytes (a cudaIpcMemHandle_t) to hand to the other ranks (any transport)
  *   ig_peer_connect  handles of ALL ranks in rank order (world x 64 bytes); own entry is ignored
  *   ig_peer_connect_local  same-process alternative (threads / tests): the contexts of all ranks, in rank order
- *   ig_a2a_loss_peer = ig_a2a_loss + publication of step `step`'s scalar; loss_prev_d (optional) <- global loss of step - 1.
- *                      `step` must increase by 1 per call on every rank (mailbox slots rotate; ranks stay within one step).
+ *   ig_a2a_loss_peer = ig_a2a_loss + publication of step `step`'s scalar; loss_prev_d (optional) <- global loss of step - lag
+ *                      (lag 1..3; 1 waits for the slowest rank's previous step every step, 2 leaves a step of slack).
+ *                      `step` must increase by 1 per call on every rank (mailbox slots rotate; ranks stay within lag steps).
  *   ig_peer_reduce   global loss of `step` into loss_d (tiny kernel; for the last step, or whenever the scalar is needed at once)
  * A rank that never delivers yields NaN after 2 s instead of a hung GPU. */
 typedef struct ig_peer ig_peer;
@@ -224,7 +225,7 @@ int ig_peer_connect(ig_peer *peer, const void *handles);
 int ig_peer_connect_local(ig_peer *const *peers, int world);
 int ig_a2a_loss_peer(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
                      float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
-                     size_t scratch_bytes, ig_peer *peer, unsigned step, float *loss_prev_d, void *stream);
+                     size_t scratch_bytes, ig_peer *peer, unsigned step, int lag, float *loss_prev_d, void *stream);
 int ig_peer_reduce(ig_peer *peer, unsigned step, float *loss_d, void *stream);
 void ig_peer_destroy(ig_peer *peer);
 

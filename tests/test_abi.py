@@ -54,7 +54,7 @@ def test_argument_validation_without_gpu():
     assert lib.ig_roi_maps(p, 0, 1, 16, 1, p, 0) == -1
     # peer exchange: rank outside the world, missing context
     assert lib.ig_peer_create(3, 2, ctypes.byref(ctypes.c_void_p())) == -1
-    assert lib.ig_a2a_loss_peer(p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, 0, 0, p, p, 1 << 20, None, 0, 0, 0) == -1
+    assert lib.ig_a2a_loss_peer(p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, 0, 0, p, p, 1 << 20, None, 0, 1, 0, 0) == -1
     # the interleaved layout is a forward-only output option
     assert lib.ig_ideal_bwd(0, p, 3, p, 1, 6, 16, 200.0, L.F_FLAT, p, p, 0) == -5
     with pytest.raises(ValueError):

@@ -31,19 +31,21 @@ def test_single_rank_exchange_equals_plain_objective():
     ref_loss, ref_g, _, _ = ops.a2a_loss(acqs, pm, tab)
     ex = igdist.PeerLossExchange(torch.device("cuda", 0))
     losses = []
-    for i in range(6):                                   # more steps than mailbox slots
+    for i in range(12):                                  # more steps than mailbox slots
         scale = 1.0 + 0.1 * i
         loss, g = ex.a2a_loss(acqs, pm * scale, tab)
         losses.append(loss.item())
         if i == 0:
-            assert torch.equal(g, ref_g) and loss.item() == ref_loss.item()
+            assert torch.equal(g, ref_g)
+            np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=1e-6)      # block partials follow the dynamic tile schedule
         else:
             assert ex.prev.item() == losses[i - 1]       # the previous step's scalar, bit for bit
     assert ex.last().item() == losses[-1]
     ex.close()
 
 
-def test_two_ranks_in_one_process():
+@pytest.mark.parametrize("lag", [1, 2])
+def test_two_ranks_in_one_process(lag):
     acqs, pm, tab = _case(nb=6)
     n_glob = acqs.numel()
     full, _, _, _ = ops.a2a_loss(acqs, pm, tab)
@@ -58,18 +60,18 @@ def test_two_ranks_in_one_process():
     shards = [(acqs[:2].contiguous(), pm[:2].contiguous(), tab[:2].contiguous()), (acqs[2:].contiguous(), pm[2:].contiguous(), tab[2:].contiguous())]
     prev = [torch.full((1,), -1.0, device="cuda") for _ in range(2)]
     local = [torch.zeros(1, device="cuda") for _ in range(2)]
-    for step in range(5):
+    for step in range(11):                               # more steps than mailbox slots
         for r, (a, p, t) in enumerate(shards):           # step-major: a rank never waits for a scalar that is not yet launched
             nb, ne, H, W, _ = a.shape
             g = torch.empty((nb, 1, H, W, 2), device="cuda")
             scr = ops.loss_scratch(a.device, nb, H * W)
             L.check(lib.ig_a2a_loss_peer(a.data_ptr(), p.data_ptr(), H * W * 2, t.data_ptr(), nb, ne, H * W, 200.0, 1.0 / n_glob, g.data_ptr(), 0, 0,
-                                         local[r].data_ptr(), scr.data_ptr(), scr.numel(), handles[r], step, prev[r].data_ptr(), st), "ig_a2a_loss_peer")
-        if step > 0:
+                                         local[r].data_ptr(), scr.data_ptr(), scr.numel(), handles[r], step, lag, prev[r].data_ptr(), st), "ig_a2a_loss_peer")
+        if step >= lag:
             assert prev[0].item() == prev[1].item()                                     # same bits on both ranks
             np.testing.assert_allclose(prev[0].item(), full.item(), rtol=2e-6)          # = the objective of the whole batch
     out = torch.zeros(1, device="cuda")
-    L.check(lib.ig_peer_reduce(handles[1], 4, out.data_ptr(), st), "ig_peer_reduce")
+    L.check(lib.ig_peer_reduce(handles[1], 10, out.data_ptr(), st), "ig_peer_reduce")
     np.testing.assert_allclose(out.item(), local[0].item() + local[1].item(), rtol=1e-7)
     # a step nobody has published: NaN after the time-out instead of a hang
     L.check(lib.ig_peer_reduce(handles[0], 1000, out.data_ptr(), st), "ig_peer_reduce")
