@@ -26,6 +26,9 @@ rv = torch.rand((nb, 1, H, W, 1), device=dev, generator=g) * 3e-3
 rm = pm[..., 1:2].contiguous()
 maps = torch.cat([up_rho * 0.1, pm], dim=1).contiguous()
 mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
+mag = torch.sqrt((acqs ** 2).sum(-1, keepdim=True)).contiguous()
+_, _, demod_s, ls_s, _ = ops.cse_mag_fwd(mag, rm.reshape(nb, 1, H, W, 1), tab)
+var5 = torch.rand((nb, 5, H, W, 2), device=dev, generator=g) * 1e-3
 targets = [
     lambda: ops.a2a_loss(acqs, pm, tab),
     lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True),
@@ -37,6 +40,8 @@ targets = [
     lambda: ops.ideal_loss(L.MODEL_MAGPHA, mp, acqs, tab),
     lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne),
     lambda: ops.get_rho_fwd(acqs, pm, tab),
+    lambda: ops.mag_regs(ls_s, demod_s, rm.reshape(nb, 1, H, W, 1), (0.1, 0.2, 0.3, 0.4)),
+    lambda: ops.roi_maps(maps, var5, "PDFF-var"),
 ]
 reps = int(os.environ.get("IG_PROFILE_REPS", "2"))
 for fn in targets:
