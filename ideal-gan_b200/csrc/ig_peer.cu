@@ -33,6 +33,12 @@ __global__ void peer_reduce_kernel(const unsigned long long *box, int world, uns
     if (threadIdx.x == 0) out[0] = peer_collect(box, world, step);
 }
 
+// stand-alone publication for the objectives whose kernels do not carry the hook (UQ, Rician, forward-model losses): one thread
+// after the loss kernel on the same stream
+__global__ void peer_publish_kernel(PeerPub peer, const float *value) {
+    if (threadIdx.x == 0) peer_exchange(peer, value[0]);
+}
+
 static int finish_connect(ig_peer *p) {
     IG_CUDA(cudaMemcpy(p->boxes_d, p->boxes_h.data(), sizeof(unsigned long long *) * p->world, cudaMemcpyHostToDevice));
     p->connected = true;
@@ -127,6 +133,15 @@ extern "C" int ig_peer_reduce(ig_peer *p, unsigned step, float *loss_d, void *st
     IG_REQUIRE(p && loss_d, IG_E_ARG, "ig_peer_reduce: null pointer");
     IG_REQUIRE(p->connected, IG_E_ARG, "ig_peer_reduce: not connected");
     peer_reduce_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p->box, p->world, step, loss_d);
+    IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ig_peer_publish(ig_peer *p, unsigned step, int lag, const float *loss_d, float *loss_prev_d, void *stream) {
+    IG_REQUIRE(p && loss_d, IG_E_ARG, "ig_peer_publish: null pointer");
+    PeerPub pub{};
+    if (int rc = peer_pub(p, step, lag, loss_prev_d, &pub)) return rc;
+    peer_publish_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pub, loss_d);
     IG_CUDA(cudaGetLastError());
     return 0;
 }

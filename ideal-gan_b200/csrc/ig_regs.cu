@@ -22,7 +22,10 @@ struct RegParams {
     float w_ad_tv, w_ls_nz, w_ls_cond, w_r2_tv;
 };
 
-__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }     // d|x|/dx with TF's sign(0) = 0
+// d|x|/dx with TF's sign(0) = 0: sign bit of x OR'ed onto [x != 0] (one compare, one select, one logic op)
+__device__ __forceinline__ float sgn(float x) {
+    return __uint_as_float((__float_as_uint(x) & 0x80000000u) | __float_as_uint(x != 0.f ? 1.0f : 0.0f));
+}
 
 // total variation of one plane at the VEC pixels starting at (row, col): forward differences are summed where they
 // exist (tf.image.total_variation: |x[1:,:] - x[:-1,:]| + |x[:,1:] - x[:,:-1]|), the gradient collects the four

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ig_peer_connect": (_i, [C.c_void_p, _fp]),
     "ig_peer_connect_local": (_i, [C.POINTER(C.c_void_p), _i]),
     "ig_a2a_loss_peer": (_i, [_fp, _fp, _l, _fp, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp, _fp, _sz, C.c_void_p, C.c_uint, _i, _fp, _fp]),
+    "ig_peer_publish": (_i, [C.c_void_p, C.c_uint, _i, _fp, _fp, _fp]),
     "ig_peer_reduce": (_i, [C.c_void_p, C.c_uint, _fp, _fp]),
     "ig_peer_destroy": (None, [C.c_void_p]),
     "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),

@@ -183,6 +183,14 @@ class PeerLossExchange:
         self.step += 1
         return loss, g_pm
 
+    def publish(self, loss, stream=None):
+        """Exchange a scalar some other objective's kernel has left in device memory (`loss`: (1,) float32, normalised by the
+        GLOBAL element count): physics_loss_a2a_uq, physics_loss_a2a_rician, physics_loss_forward.  One thread on the same stream;
+        self.prev receives the global value of the step `lag` steps back."""
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._L.check(self._L.load().ig_peer_publish(self.handle, self.step, self.lag, loss.data_ptr(), self.prev.data_ptr(), st), "ig_peer_publish")
+        self.step += 1
+
     def last(self, stream=None):
         """Global loss of the most recent step (launches the one-warp reduction; waits for the peers on the device)."""
         if self.step == 0:

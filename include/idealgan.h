@@ -215,6 +215,8 @@ int ig_maps_from_flat(const float *flat_d, int nb, int nv, int mode, float *maps
  *   ig_a2a_loss_peer = ig_a2a_loss + publication of step `step`'s scalar; loss_prev_d (optional) <- global loss of step - lag
  *                      (lag 1..3; 1 waits for the slowest rank's previous step every step, 2 leaves a step of slack).
  *                      `step` must increase by 1 per call on every rank (mailbox slots rotate; ranks stay within lag steps).
+ *   ig_peer_publish  the same exchange for a scalar already in device memory (any other objective: ig_a2a_uq_loss,
+ *                      ig_a2a_rician_loss, ig_ideal_loss): one thread, launched after the loss kernel on the same stream
  *   ig_peer_reduce   global loss of `step` into loss_d (tiny kernel; for the last step, or whenever the scalar is needed at once)
  * A rank that never delivers yields NaN after 2 s instead of a hung GPU. */
 typedef struct ig_peer ig_peer;
@@ -226,6 +228,7 @@ int ig_peer_connect_local(ig_peer *const *peers, int world);
 int ig_a2a_loss_peer(const float *acqs_d, const float *pm_d, long pm_bstride, const float *tab_d, int nb, int ne, int nv,
                      float r2_sc, float inv_n, float *g_pm_d, float *rho_d, float *shat_d, float *loss_d, void *scratch_d,
                      size_t scratch_bytes, ig_peer *peer, unsigned step, int lag, float *loss_prev_d, void *stream);
+int ig_peer_publish(ig_peer *peer, unsigned step, int lag, const float *loss_d, float *loss_prev_d, void *stream);
 int ig_peer_reduce(ig_peer *peer, unsigned step, float *loss_d, void *stream);
 void ig_peer_destroy(ig_peer *peer);
 

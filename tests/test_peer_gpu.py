@@ -88,3 +88,38 @@ def test_peer_argument_errors():
     out = torch.zeros(1, device="cuda")
     assert lib.ig_peer_reduce(h, 0, out.data_ptr(), 0) == -1                            # not connected
     lib.ig_peer_destroy(h)
+
+
+def test_publish_for_the_other_objectives():
+    """ig_peer_publish: the exchange for a scalar that is already on the device (here the uncertainty-aware objective's)."""
+    acqs, pm, tab = _case(nb=4)
+    nb, ne, H, W, _ = acqs.shape
+    rng = np.random.default_rng(4)
+    pv = torch.from_numpy(rng.uniform(1e-5, 4e-3, (nb, 1, H, W, 1)).astype(np.float32)).cuda()
+    rv = torch.from_numpy(rng.uniform(1e-5, 3e-3, (nb, 1, H, W, 1)).astype(np.float32)).cuda()
+    rm = pm[..., 1:2].contiguous()
+    lib = L.load()
+    handles = (ctypes.c_void_p * 2)()
+    for r in range(2):
+        h = ctypes.c_void_p()
+        L.check(lib.ig_peer_create(r, 2, ctypes.byref(h)), "ig_peer_create")
+        handles[r] = h
+    L.check(lib.ig_peer_connect_local(handles, 2), "ig_peer_connect_local")
+    st = torch.cuda.current_stream().cuda_stream
+    inv_n = 1.0 / acqs.numel()
+    whole = ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab, inv_n=inv_n)[0]
+    prev = [torch.zeros(1, device="cuda") for _ in range(2)]
+    parts = []
+    for step in range(3):
+        parts = []
+        for r, sl in enumerate((slice(0, 1), slice(1, 4))):           # ragged shards
+            loc = ops.a2a_uq_loss(acqs[sl].contiguous(), pm[sl].contiguous(), pv[sl].contiguous(), rm[sl].contiguous(), rv[sl].contiguous(),
+                                  tab[sl].contiguous(), inv_n=inv_n)[0]
+            parts.append(loc)
+            L.check(lib.ig_peer_publish(handles[r], step, 1, loc.data_ptr(), prev[r].data_ptr(), st), "ig_peer_publish")
+        if step:
+            assert prev[0].item() == prev[1].item()
+            np.testing.assert_allclose(prev[0].item(), whole.item(), rtol=3e-6)
+    assert lib.ig_peer_publish(handles[0], 3, 0, parts[0].data_ptr(), prev[0].data_ptr(), st) == -1     # lag outside [1, 3]
+    for r in range(2):
+        lib.ig_peer_destroy(handles[r])
