@@ -168,6 +168,23 @@ def main():
             s1 = ops.ideal_fwd(L.MODEL_WFPM, maps, t1, ne)
             r1, _ = ops.get_rho_fwd(s1, pm1, t1)
     add("graph[tables+fwd+solve]", "C1 single slice, CUDA-graph replay (latency)", 1, 384 * 384, ne, 144, graph.replay)
+    # C4 at the script's own batch size (train-IDEAL-single.py: 3 slices): tables + fused mag/phase objective from a CUDA graph
+    nb4 = 3
+    rng4 = np.random.default_rng(4)
+    mp4 = torch.from_numpy(synth.magpha_maps(nb4, 384, 384, rng4)).to(dev)
+    te4 = torch.from_numpy(np.ascontiguousarray(synth.te_random(nb4, ne, rng4, te_ini_d=0.4e-3, d_te_min=0.9e-3, d_te_d=0.3e-3)[:, :, 0])).to(dev)
+    a4 = ops.ideal_fwd(L.MODEL_MAGPHA, mp4, ops.gen_tables(te4, 1.5), ne)
+    a4 = torch.where(a4 != 0, a4 + 0.02 * torch.randn(a4.shape, device=dev, generator=g), torch.zeros_like(a4)).contiguous()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            ops.ideal_loss(L.MODEL_MAGPHA, mp4, a4, ops.gen_tables(te4, 1.5))
+        side.synchronize()
+        graph4 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph4, stream=side):
+            l4, g4, _ = ops.ideal_loss(L.MODEL_MAGPHA, mp4, a4, ops.gen_tables(te4, 1.5))
+    add("graph[tables+ideal_loss magpha]", "C4 at nb = 3 (train-IDEAL-single), CUDA-graph replay (latency)", nb4, 384 * 384, ne, 8 * ne + 32 + 32, graph4.replay)
+    add("ig_ideal_loss[magpha]", "C4 at nb = 3 through the Python wrappers (latency)", nb4, 384 * 384, ne, 8 * ne + 32 + 32,
+        lambda: ops.ideal_loss(L.MODEL_MAGPHA, mp4, a4, ops.gen_tables(te4, 1.5)))
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
 
