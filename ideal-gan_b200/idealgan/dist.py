@@ -19,12 +19,15 @@ def shard_bounds(n, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def shard(tensor, rank=None, world=None):
-    """This rank's slice of a tensor along the batch axis."""
+def shard(tensor, rank=None, world=None, axis=0):
+    """This rank's slice of a tensor along the batch axis -- or, with axis = 2, along the image rows H of a (nb, rows, H, W, c)
+    tensor: for batches smaller than the number of GPUs (config 1: one slice, config 4: three) the voxels of a slice are split
+    instead of the slices; every operator of the path is pointwise in the voxel, so there is no halo.  The
+    echo times stay whole on every rank."""
     rank = dist.get_rank() if rank is None else rank
     world = dist.get_world_size() if world is None else world
-    a, b = shard_bounds(tensor.shape[0], rank, world)
-    return tensor[a:b]
+    a, b = shard_bounds(tensor.shape[axis], rank, world)
+    return tensor.narrow(axis, a, b - a)
 
 
 def sharded_physics_loss(loss_fn, acqs_shard, maps_shard, te_shard, global_elements, group=None, **kw):
@@ -38,17 +41,19 @@ def sharded_physics_loss(loss_fn, acqs_shard, maps_shard, te_shard, global_eleme
     return total.reshape(()), local
 
 
-def gather_batch(tensor_shard, global_nb, group=None):
+def gather_batch(tensor_shard, global_nb, group=None, axis=0):
     """Optional all-gather of per-shard results (e.g. gradient maps) into one tensor on every rank.  Shards may be
-    ragged (global_nb % world != 0): they are padded to the largest shard for the collective and trimmed after."""
+    ragged (global_nb % world != 0): they are padded to the largest shard for the collective and trimmed after.
+    axis = 2 reassembles row shards (see shard); global_nb is then the full extent of that axis."""
     world = dist.get_world_size(group)
     sizes = [b - a for a, b in (shard_bounds(global_nb, r, world) for r in range(world))]
     longest = max(sizes)
-    padded = tensor_shard.new_zeros((longest,) + tuple(tensor_shard.shape[1:]))
-    padded[: tensor_shard.shape[0]] = tensor_shard
+    moved = tensor_shard.movedim(axis, 0)
+    padded = moved.new_zeros((longest,) + tuple(moved.shape[1:]))
+    padded[: moved.shape[0]] = moved
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0).movedim(0, axis).contiguous()
 
 
 class AsyncLossReducer:

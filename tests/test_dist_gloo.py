@@ -138,3 +138,37 @@ def test_peer_exchange_setup_fails_on_every_rank_together():
         assert len(out) == world
         for r in range(world):
             assert "set-up failed" in out[r], out[r]
+
+
+def _row_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from oracle import ideal_oracle as orc
+        rng = np.random.default_rng(1)
+        nb, H, W = 1, 9, 6                                                 # one slice, fewer slices than ranks: split the rows (ragged)
+        maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+        te = torch.from_numpy(synth.te_random(nb, 6, rng))
+        acqs = torch.from_numpy(synth.add_noise(orc.IDEAL_model(torch.from_numpy(maps), [1.5, te]).numpy(), rng))
+        pm = torch.from_numpy(np.ascontiguousarray(maps[:, 2:3]) * np.float32(0.9))
+        p_full = pm.clone().requires_grad_(True)
+        full = _oracle_loss(acqs, p_full, te, 1.0 / acqs.numel())
+        (g_full,) = torch.autograd.grad(full, [p_full])
+        p_loc = igdist.shard(pm, axis=2).clone().requires_grad_(True)
+        total, local = igdist.sharded_physics_loss(_oracle_loss, igdist.shard(acqs, axis=2).contiguous(), p_loc, te, acqs.numel())
+        (g_loc,) = torch.autograd.grad(local, [p_loc])
+        gathered = igdist.gather_batch(g_loc, H, axis=2)
+        out[rank] = bool(abs(total.item() - full.item()) <= 1e-6 * full.item() and torch.allclose(gathered, g_full, rtol=1e-5, atol=1e-9)
+                         and gathered.shape == g_full.shape)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharding_for_batches_smaller_than_the_world():
+    """for nb < #GPUs (config 1, config 4 at nb = 3) the rows H are split instead; pointwise operators need no halo."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_row_worker, args=(2, port, out), nprocs=2, join=True)
+        assert dict(out) == {0: True, 1: True}
