@@ -85,3 +85,17 @@ def test_host_tables_match_reference(golden, case):
     full = tab[:, :L.TAB_AP_OFF].reshape(nb, L.MAX_NE, L.REC_FLOATS)
     assert not full[:, ne:].any()                                                # zero padding beyond ne
     assert np.all(tab[:, L.TAB_META_OFF] == ne)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/idealgan.h is the boundary a C (cgo, JNI, Julia ccall ...) binding compiles against: it must be valid C99 on its own."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use.c"
+    src.write_text('#include "idealgan.h"\n'
+                   "int probe(void) { ig_peer *p = 0; ig_ctx *c = 0; (void)p; (void)c; return IG_VERSION + IG_E_ARG + (int)sizeof(size_t); }\n")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                   check=True, capture_output=True, text=True)
