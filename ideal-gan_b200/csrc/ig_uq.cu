@@ -176,6 +176,10 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
     __shared__ SampleTab<NE> T;
     __shared__ float4 btab[kBesselRows * 3];
     stage_bessel_table(btab);            // visible after the __syncthreads of the first stage_table
+    // up to 8 echoes: the decay and the observed magnitude of each echo wait for pass 2 in the thread's own shared-memory slots
+    // instead of 4 registers per echo (24 at ne = 6, where the kernel sat at the 128-register cap with spills)
+    constexpr bool PARK = lanes<V>::n == 2 && NE <= 8;
+    __shared__ float4 park[PARK ? NE * kThreads : 1];
     const int nv = p.nv, ne = p.ne;
     constexpr int L = lanes<V>::n;
     const int tiles_ps = (nv + kThreads * L - 1) / (kThreads * L);
@@ -229,6 +233,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
                     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));
                     lane_set(ys[e], l, copysignf(mag, re != 0.f ? 1.0f : -1.0f));
                 }
+                if constexpr (PARK) park[e * kThreads + threadIdx.x] = make_float4(lane_get(dec[e], 0), lane_get(dec[e], 1), lane_get(ys[e], 0), lane_get(ys[e], 1));
             }
         }
         UqAcc acc[L];
@@ -251,8 +256,14 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
                 V sc = zero;       // g_nu d / |yhat|
                 if constexpr (L == 2) {
                     const pk ra = mk(a2.d.x > 1e-30f ? rsqrt_ftz(a2.d.x) : 0.f, a2.d.y > 1e-30f ? rsqrt_ftz(a2.d.y) : 0.f);
-                    const pk dra = vmul(dec[e], ra);
-                    const pk g = rician_echo(btab, R.te, a2, ys[e], vmul(dra, a2), sp2, mu2, sr2, rem, acc2);
+                    pk de = dec[e], yo = ys[e];
+                    if constexpr (PARK) {
+                        const float4 q = park[e * kThreads + threadIdx.x];
+                        de = mk(q.x, q.y);
+                        yo = mk(q.z, q.w);
+                    }
+                    const pk dra = vmul(de, ra);
+                    const pk g = rician_echo(btab, R.te, a2, yo, vmul(dra, a2), sp2, mu2, sr2, rem, acc2);
                     sc = vmul(g, dra);
                 } else {
 #pragma unroll
