@@ -133,7 +133,8 @@ def test_bridge_fused_objective_and_unused_input_gradient(fake_tf):
     loss_tf = op(FakeTensor(acqs), FakeTensor(pm))
     p = pm.clone().requires_grad_(True)
     loss = TO.physics_loss_a2a(acqs, p, te)
-    assert loss_tf._t.item() == loss.item()
+    # the ring kernel's block partials follow its dynamic tile schedule: the scalar repeats to ~1e-7, not bit for bit
+    np.testing.assert_allclose(loss_tf._t.item(), loss.item(), rtol=1e-6)
     (_, grad_fn), = fake_tf.recorded
     ga_tf, gp_tf = grad_fn(FakeTensor(torch.ones((), device="cuda")))
     (gp,) = torch.autograd.grad(loss, [p])
