@@ -145,6 +145,17 @@ __device__ __forceinline__ void unit_phasor(pk turns, pk &c, pk &s) {
     c = mk(__cosf(r.x), __cosf(r.y));
     s = mk(__sinf(r.x), __sinf(r.y));
 }
+// Phase already in radians, no explicit reduction: sin.approx / cos.approx are FMUL by 1/(2 pi) + MUFU.SIN/COS, and the MUFU
+// takes its argument in turns and drops the integer part itself, so the only cost of |x| > pi is the fp32 spacing of x
+// (|x| <= 25 rad on this path: 2^-20 rad).  Saves the 3 FADD2 + FMUL2 of the exact reduction per echo.
+__device__ __forceinline__ void unit_phasor_rad(float rad, float &c, float &s) {
+    c = __cosf(rad);
+    s = __sinf(rad);
+}
+__device__ __forceinline__ void unit_phasor_rad(pk rad, pk &c, pk &s) {
+    c = mk(__cosf(rad.d.x), __cosf(rad.d.y));
+    s = mk(__sinf(rad.d.x), __sinf(rad.d.y));
+}
 __device__ __forceinline__ pk fast_ex2(pk x) { return mk(fast_ex2(x.d.x), fast_ex2(x.d.y)); }
 __device__ __forceinline__ float vrelu(float x) { return fmaxf(x, 0.f); }
 __device__ __forceinline__ pk vrelu(pk x) { return mk(fmaxf(x.d.x, 0.f), fmaxf(x.d.y, 0.f)); }
@@ -202,7 +213,8 @@ struct __align__(16) EchoRec {
     float c_re, c_im;
     float pw_re, pw_im, pf_re, pf_im;
     float tpw_re, tpw_im, tpf_re, tpf_im;   // te * M^+ rows
-    float pad0, pad1;
+    float kphi_rad; // 2 pi te fm_sc         : phase in RADIANS per unit of the phi/300 map (one rounding, from fp64)
+    float pad1;
 };
 static_assert(sizeof(EchoRec) == IG_REC_FLOATS * sizeof(float), "echo record layout");
 
@@ -239,9 +251,10 @@ template <int NE, typename V> __device__ __forceinline__ Mod<V> modulator(const 
     m.dinv = fast_ex2(vneg(lg));
     return m;
 }
-template <typename V, bool BIP = true> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
+template <typename V, bool BIP = true, bool RAD = false> __device__ __forceinline__ Mod<V> modulator_rec(const EchoRec &R, V phi_t, V r2, V bturn) {
     Mod<V> m;
     if constexpr (BIP) unit_phasor(vfma(R.sgn, bturn, vmul(R.kphi, phi_t)), m.c, m.s);
+    else if constexpr (RAD) unit_phasor_rad(vmul(R.kphi_rad, phi_t), m.c, m.s);
     else unit_phasor(vmul(R.kphi, phi_t), m.c, m.s);
     const V lg = vmul(R.kdec, r2);
     m.d = fast_ex2(lg);
@@ -380,6 +393,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// generic-proxy writes to shared memory made visible to the async proxy (TMA) before the stage is handed back to the producer
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -418,6 +433,15 @@ template <typename F> inline int dispatch_ne(int ne, F &&f) {
     if (ne <= 12) return f(std::integral_constant<int, 12>{});
     return f(std::integral_constant<int, 16>{});
 }
+
+// Operators on the generic TMA ring (ig_ring_ops.cu).  IG_E_UNSUPPORTED = shape / alignment not covered: run the plain kernel.
+int a2a_bwd_ring(const float *acqs, const float *pm, long pm_bstride, const float *tab, int nb, int ne, int nv, float r2_sc, const float *g_rho,
+                 const float *g_shat, float *g_acqs, float *g_pm, cudaStream_t st);
+int magpha_loss_ring(const float *maps, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *gmaps, float *shat,
+                     float *loss, void *scratch, cudaStream_t st);
+int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
+                         const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
+                         float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st);
 
 inline dim3 grid_for(int nb, int nv, int vpt) {
     const int per_block = kThreads * vpt;

@@ -14,6 +14,14 @@
 
 namespace ig {
 
+// The fused objectives form the phase in radians and hand it to sin.approx / cos.approx without the exact turn reduction: 4 fewer FP32
+// lane-operations per voxel-echo on a kernel bound by the FMA pipe (measured 0.1192 -> 0.1131 ms masked, 0.1395 -> 0.1297 ms
+// unmasked at 64 x 384 x 384 x 6; error against the fp64 oracle unchanged, profiles/history_r02.md).  -DIG_PHASE_RAD=0 restores it.
+#ifndef IG_PHASE_RAD
+#define IG_PHASE_RAD 1
+#endif
+constexpr bool kPhaseRad = IG_PHASE_RAD != 0;
+
 struct SolveParams {
     const float *acqs, *pm, *bip, *tab;
     const float *g_rho, *g_demod, *g_shat;
@@ -509,7 +517,7 @@ template <int NE, typename V, bool OUTPUTS, int MINB> __global__ void __launch_b
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
                 const EchoRec R = T.r[e];
-                const Mod<V> m = modulator_rec(R, phi_t, r2, zero);
+                const Mod<V> m = modulator_rec<V, false, kPhaseRad>(R, phi_t, r2, zero);
                 if constexpr (OUTPUTS) mods[e] = m;
                 d2[e] = vmul(m.d, m.d);
                 y[e] = demod_raw(vmul(m.c, m.dinv), vmul(m.s, m.dinv), raw[e]);
@@ -825,7 +833,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     for (int e = 0; e < NE; ++e) {
                         if (EXACT || e < ne) {
                             const EchoRec R = T.r[e];
-                            const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                            const Mod<pk> m = modulator_rec<pk, false, kPhaseRad>(R, phi_t, r2s, zero);
                             if constexpr (MODE == 1) d2[e] = vmul(m.d, m.d);
                             RawEcho<pk> raw;
                             raw.v = e == 0 ? raw0 : sraw[e * kPlaneF4];
@@ -914,7 +922,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                             for (int e = 0; e < NE; ++e) {
                                 if (EXACT || e < ne) {
                                     const EchoRec R = T.r[e];
-                                    const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                                    const Mod<pk> m = modulator_rec<pk, false, kPhaseRad>(R, phi_t, r2s, zero);
                                     const float4 q = __ldcs(reinterpret_cast<const float4 *>(p.acqs + (static_cast<size_t>(b) * ne + e) * nv * 2) + (v0 >> 1));
                                     const cx<pk> ye = demod(m, cx<pk>{mk(q.x, q.z), mk(q.y, q.w)});
                                     cmac(rw, R.pw_re, R.pw_im, ye);
@@ -926,7 +934,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                                 for (int e = 0; e < NE; ++e) {
                                     if (EXACT || e < ne) {
                                         const EchoRec R = T.r[e];
-                                        const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                                        const Mod<pk> m = modulator_rec<pk, false, kPhaseRad>(R, phi_t, r2s, zero);
                                         st_cx(p.shat + (static_cast<size_t>(b) * ne + e) * nv * 2, v0, remod(m, caffine(rw, R.c_re, R.c_im, rf)));
                                     }
                                 }
@@ -989,7 +997,7 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     for (int e = 0; e < NE; ++e) {
                         if (EXACT || e < ne) {
                             const EchoRec R = T.r[e];
-                            const Mod<pk> m = modulator_rec<pk, false>(R, phi_t, r2s, zero);
+                            const Mod<pk> m = modulator_rec<pk, false, kPhaseRad>(R, phi_t, r2s, zero);
                             d2[e] = vmul(m.d, m.d);
                             RawEcho<pk> raw;
                             raw.v = sraw[e * kPlaneF4];              // second read of the stage: cheaper than 24 live registers
@@ -1040,6 +1048,9 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
                     }
                 }
             }
+            // consumers that parked y / Wp in the stage wrote it through the generic proxy; the producer refills the same bytes
+            // through the async proxy (TMA), and the PTX memory model orders the two only across a proxy fence
+            if constexpr (MODE == 0 || OUT) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);                        // this warp no longer touches the stage
         }
@@ -1306,6 +1317,10 @@ extern "C" int ig_a2a_bwd(const float *acqs_d, const float *pm_d, long pm_bstrid
     p.flags = flags; p.g_rho = g_rho_d; p.g_shat = g_shat_d; p.g_acqs = g_acqs_d; p.g_pm = g_pm_d;
     const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, g_rho_d, g_shat_d, g_acqs_d, g_pm_d});
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (packed && !(flags & IG_F_ONLY_MAG)) {        // TMA ring (128-voxel rows, <= 8 echoes): ig_ring_ops.cu
+        const int rc = a2a_bwd_ring(acqs_d, pm_d, pm_bstride, tab_d, nb, ne, nv, r2_sc, g_rho_d, g_shat_d, g_acqs_d, g_pm_d, st);
+        if (rc != IG_E_UNSUPPORTED) return rc;
+    }
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         return launch_pair(packed, p, st, a2a_bwd_kernel<NE, pk>, a2a_bwd_kernel<NE, float>);

@@ -91,7 +91,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
             for (int e = 0; e < NE; ++e) {
                 if (e < ne) {
                     const EchoRec R = T.r[e];
-                    const Mod<V> m = modulator_rec<V, false>(R, phi_t, r2, zero);
+                    const Mod<V> m = modulator_rec<V, false, true>(R, phi_t, r2, zero);
                     d2[e] = vmul(m.d, m.d);
                     y[e] = demod(m, S[e]);
                     cmac(rw, R.pw_re, R.pw_im, y[e]);
@@ -219,7 +219,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads, 2) a2a
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
                 const EchoRec R = T.r[e];
-                const Mod<V> m = modulator_rec<V, false>(R, phi_t, r2, zero);
+                const Mod<V> m = modulator_rec<V, false, true>(R, phi_t, r2, zero);
                 const cx<V> y = demod(m, S[e]);
                 cmac(rw, R.pw_re, R.pw_im, y);
                 cmac(rf, R.pf_re, R.pf_im, y);
@@ -360,6 +360,11 @@ extern "C" int ig_a2a_rician_loss(const float *acqs_d, const float *pm_d, long p
                           static_cast<const void *>(g_phi_var_d), static_cast<const void *>(g_r2_mean_d), static_cast<const void *>(g_r2_var_d)})
         packed = packed && (!q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (packed) {                                    // TMA ring (128-voxel rows, <= 8 echoes): ig_ring_ops.cu
+        const int rc = a2a_rician_loss_ring(acqs_d, pm_d, pm_bstride, phi_var_d, r2_mean_d, r2_var_d, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d,
+                                            g_phi_var_d, g_r2_mean_d, g_r2_var_d, rho_d, loss_d, scratch_d, st);
+        if (rc != IG_E_UNSUPPORTED) return rc;
+    }
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         int grid = 1;

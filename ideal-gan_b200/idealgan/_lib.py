@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidealgan.so")
+# IDEALGAN_LIB: another build of the same library (kernel A/B experiments, `make SUFFIX=_x EXTRA=-D...`); the product is libidealgan.so
+LIB_PATH = os.environ.get("IDEALGAN_LIB") or os.path.join(_HERE, "libidealgan.so")
 
 MAX_NE = 16
 REC_FLOATS = 16

@@ -53,7 +53,8 @@ enum {
     IG_REC_TPW_RE = 10,  /* te * M^+[0,e]                                                             */
     IG_REC_TPW_IM = 11,
     IG_REC_TPF_RE = 12,  /* te * M^+[1,e]                                                             */
-    IG_REC_TPF_IM = 13
+    IG_REC_TPF_IM = 13,
+    IG_REC_KPHI_RAD = 14 /* 2 pi te fm_sc: phase in RADIANS per unit of the phi/300 map                */
 };
 
 enum { IG_MODEL_WFPM = 0, IG_MODEL_FFPD = 1, IG_MODEL_MAGPHA = 2 };
