@@ -10,8 +10,13 @@ SURVEY §8d (disc-masked random maps -> forward model -> N(0, 0.02^2) noise).
     python bench.py --impl reference          (the reference's op-chain algorithm on the host cores, torch-CPU port)
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
-`e2e` = the same objective through the host-buffer C-ABI call (pinned host inputs, H2D + kernel + D2H per step);
-`roofline` = algorithmic bytes of the fused kernel / its measured duration against MEASURED_PEAKS.json.
+`e2e` = the same objective through the host-buffer C-ABI call (pinned host inputs, H2D + kernel + D2H per step) with the
+bare-copy ceiling of this host measured beside it; `roofline` = algorithmic bytes of the fused kernel / its measured duration
+against MEASURED_PEAKS.json, for the disc-masked batch (`frac`) and for an unmasked one (`frac_unmasked`);
+`dropin` = the same step as an UNMODIFIED train-IDEAL-unsup.py reaches it (wf.acq_to_acq -> where -> MSE -> autograd);
+`configs` = BASELINE.json's other four configurations (C1, C3, C4, C5), each through the C ABI with CUDA events; C5 is
+sharded over the ranks under --gpus N.  The CPU arm prefers the real reference under TensorFlow (oracle/tf_ref.py) and says
+which implementation ran in `cpu_baseline.kind` ("tf" | "port").
 """
 import argparse
 import ctypes
@@ -113,12 +118,53 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's algorithm (batched complex op chain + autograd) on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_port_step(acqs, pm, te):
-    from oracle import ideal_oracle as orc
-    p = pm.clone().requires_grad_(True)
-    loss, _, _ = orc.physics_loss_a2a(acqs, p, te=te, field=FIELD, r2_sc=R2_SC)
-    (g,) = torch.autograd.grad(loss, [p])
-    return loss, g
+def reference_kind():
+    """("tf", version) when the real reference can run under TensorFlow on this machine, else ("port", why)."""
+    try:
+        from oracle import tf_ref
+        tf = tf_ref.real_tensorflow()
+        if tf is None:
+            return "port", "TensorFlow is not importable here"
+        if tf_ref.find_reference() is None:
+            return "port", "TensorFlow present but no reference checkout (IDEALGAN_REFERENCE, /root/reference, baseline/_ref)"
+        return "tf", f"TensorFlow {tf.__version__}"
+    except Exception as e:      # noqa: BLE001
+        return "port", f"TensorFlow probe failed: {e!r}"
+
+
+class CpuArm:
+    """The reference's C2 step on the host cores: the reference's own wflib under TensorFlow (@tf.function + GradientTape, all
+    intra-op threads) when that can run, else the oracle's torch-CPU port of the same op chain."""
+
+    def __init__(self):
+        self.kind, self.why = reference_kind()
+        self.cores = os.cpu_count() or 1
+        if self.kind == "tf":
+            from oracle import tf_ref
+            self.ref = tf_ref.Reference()
+            self.step_fn = self.ref.c2_step_fn(field=FIELD, r2_sc=R2_SC, graph=True)
+        else:
+            torch.set_num_threads(self.cores)
+
+    def prepare(self, acqs, pm, te):
+        if self.kind == "tf":
+            return tuple(self.ref.T(x.numpy()) for x in (acqs, pm, te))
+        return acqs, pm, te
+
+    def step(self, acqs, pm, te):
+        if self.kind == "tf":
+            loss, g = self.step_fn(acqs, pm, te)
+            return float(loss), g
+        from oracle import ideal_oracle as orc
+        p = pm.clone().requires_grad_(True)
+        loss, _, _ = orc.physics_loss_a2a(acqs, p, te=te, field=FIELD, r2_sc=R2_SC)
+        (g,) = torch.autograd.grad(loss, [p])
+        return loss, g
+
+    def describe(self, nb):
+        what = (f"reference wflib.acq_to_acq + tf.where + MSE + tf.GradientTape under {self.why}, @tf.function" if self.kind == "tf" else
+                "oracle/ideal_oracle.py physics_loss_a2a + torch autograd, complex64 (the reference's op chain; " + self.why + ")")
+        return f"{nb} of the {NB} slices per step ({H}x{W}x{NE}), {what}"
 
 
 def cpu_sample(nb, seed=1234):
@@ -139,33 +185,33 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    arm = CpuArm()
     # bounded sample: as many slices per step (8, 4, 2 or 1) as keep the whole run within ~150 s
     nb = 8
     acqs, pm, te = cpu_sample(nb)
-    cpu_port_step(acqs, pm, te)
+    x = arm.prepare(acqs, pm, te)
+    arm.step(*x)
     c0 = time.perf_counter()
-    cpu_port_step(acqs, pm, te)
+    arm.step(*x)
     per_step = time.perf_counter() - c0
     while nb > 1 and per_step * (args.steps + args.warmup) > 150.0:
         nb //= 2
         per_step /= 2
-    acqs, pm, te = acqs[:nb].contiguous(), pm[:nb].contiguous(), te[:nb].contiguous()
+    x = arm.prepare(acqs[:nb].contiguous(), pm[:nb].contiguous(), te[:nb].contiguous())
     for _ in range(max(args.warmup, 1)):
-        cpu_port_step(acqs, pm, te)
+        arm.step(*x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_step(acqs, pm, te)
+        arm.step(*x)
     dt = time.perf_counter() - t0
     value = nb * H * W * NE * args.steps / dt
-    sample = f"{nb} of the {NB} slices per step ({H}x{W}x{NE}), oracle/ideal_oracle.py physics_loss_a2a + torch autograd, complex64"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference is TensorFlow op chains; TF is not installable here, so its "
-                       "algorithm is timed as the torch-CPU port held to the reference's vectors (tests/test_oracle_golden.py)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "reference_arm": arm.kind, "note": arm.why if arm.kind == "tf" else
+                       "reference is TensorFlow op chains; " + arm.why + ", so its algorithm is timed as the torch-CPU port held to "
+                       "the reference's vectors (tests/test_oracle_golden.py)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe(nb)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -173,25 +219,266 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
-def build_device_inputs(device, seed):
+def build_device_inputs(device, seed, nb=NB, h=H, w=W, masked=True, te=None):
     """Synthetic C2 batch generated on the device with this repo's own forward kernel (SURVEY §8d recipe)."""
     from idealgan import _lib as L
     from idealgan import ops, synth
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    mask = torch.from_numpy(synth.disc_mask(H, W).astype(np.float32)).to(device)[None, None, :, :, None]
-    maps = torch.empty((NB, 3, H, W, 2), device=device)
-    maps[:, :2] = torch.rand((NB, 2, H, W, 2), device=device, generator=g) - 0.5
-    maps[:, 2, :, :, 0] = 2.0 * torch.rand((NB, H, W), device=device, generator=g) - 1.0
-    maps[:, 2, :, :, 1] = torch.rand((NB, H, W), device=device, generator=g)
-    maps *= mask
-    te = torch.from_numpy(synth.te_orig(NB, NE)).to(device)
+    maps = torch.empty((nb, 3, h, w, 2), device=device)
+    maps[:, :2] = torch.rand((nb, 2, h, w, 2), device=device, generator=g) - 0.5
+    maps[:, 2, :, :, 0] = 2.0 * torch.rand((nb, h, w), device=device, generator=g) - 1.0
+    maps[:, 2, :, :, 1] = torch.rand((nb, h, w), device=device, generator=g)
+    if masked:
+        maps *= torch.from_numpy(synth.disc_mask(h, w).astype(np.float32)).to(device)[None, None, :, :, None]
+    te = torch.from_numpy(synth.te_orig(nb, NE) if te is None else te).to(device)
     tab = ops.gen_tables(te, FIELD)
     clean = ops.ideal_fwd(L.MODEL_WFPM, maps, tab, NE, R2_SC)
     noise = 0.02 * torch.randn(clean.shape, device=device, generator=g)
     acqs = torch.where(clean != 0, clean + noise, torch.zeros_like(clean)).contiguous()
     pm = (maps[:, 2:3] * 0.95).contiguous()          # an imperfect (phi, R2*) estimate, as a network would give
-    return acqs, pm, te
+    return acqs, pm, te, maps
+
+
+def event_times(fn, reps, warm=3, stream=None):
+    """CUDA-event duration of each of `reps` calls of fn() on the current stream (ms), after `warm` untimed calls."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def dropin_leg(acqs, pm, te_dev, reps):
+    """The step exactly as train-IDEAL-unsup.py:214-218,236,255 writes it, on the drop-in `wflib` with framework autograd --
+    what an unmodified script reaches -- next to the one-line edit (`physics_loss_a2a`, the fused kernel behind autograd)."""
+    import wflib as wf
+    from idealgan import torch_ops as TO
+    p = pm.clone().requires_grad_(True)
+    units = acqs.shape[0] * acqs.shape[2] * acqs.shape[3] * NE
+
+    def script_step():
+        p.grad = None
+        A2B_WF, A2B2A = wf.acq_to_acq(acqs, p, te=te_dev, field=FIELD)                    # :216
+        A2B2A = torch.where(acqs != 0.0, A2B2A, 0.0)                                      # :218
+        loss = torch.mean(torch.square(acqs - A2B2A))                                     # :236 tf.losses.MeanSquaredError
+        loss.backward()                                                                   # :255 t.gradient
+        return loss
+
+    def fused_step():
+        p.grad = None
+        loss = TO.physics_loss_a2a(acqs, p, te_dev, FIELD, R2_SC)
+        loss.backward()
+        return loss
+
+    l_script, l_fused = script_step().item(), fused_step().item()
+    g_script = p.grad.clone()
+    script_step()
+    g_rel = float((p.grad - g_script).abs().max() / g_script.abs().max())
+    t_script = float(np.median(event_times(script_step, reps)))
+    t_fused = float(np.median(event_times(fused_step, reps)))
+    return {"what": "train-IDEAL-unsup.py:214-218,236,255 unmodified on the drop-in wflib: wf.acq_to_acq -> torch.where -> MSE -> "
+                    "autograd (device-resident, same batch, echo-time table cached)",
+            "ms_per_step": t_script, "value": units / (t_script * 1e-3), "unit": UNIT,
+            "kernels": "ig_a2a_fwd (120 B/voxel) + framework where / sub / square / mean and their autograd mirror images + ig_a2a_bwd (112 B/voxel)",
+            "one_line_edit": {"what": "torch_ops.physics_loss_a2a(...).backward(): the fused kernel behind autograd (INTEGRATION.md §1)",
+                              "ms_per_step": t_fused, "value": units / (t_fused * 1e-3)},
+            "loss": l_script, "loss_fused": l_fused, "grad_rel_diff_between_runs": g_rel}
+
+
+def configs_leg(device, peak, reps):
+    """BASELINE.json configs C1, C3, C4 through the C ABI (idealgan.ops is allocation + one ctypes call per entry point), CUDA
+    events on the launching stream; fractions are algorithmic bytes / median duration / measured HBM peak."""
+    from idealgan import _lib as L
+    from idealgan import ops, synth
+    lib = L.load()
+    out = {}
+    rng = np.random.default_rng(1234)
+
+    def frac(bytes_per_voxel, nvox, ms):
+        return bytes_per_voxel * nvox / (ms * 1e-3) / 1e9 / peak
+
+    def graph_us(body, n=200):
+        body()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            body()
+        for _ in range(5):
+            gr.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return 1e3 * a.elapsed_time(b) / n
+
+    # ---- C1: IDEAL_Layer forward + LS solve, one 384 x 384 x 6 slice: a latency case ------------------------------------
+    import wflib as wf
+    acqs1, pm1, te1, maps1 = build_device_inputs(device, 11, nb=1)
+    layer = wf.IDEAL_Layer(field=FIELD)
+
+    def c1_wrappers():
+        sig = layer(maps1, te=te1, training=False)
+        return wf.get_rho(sig, maps1[:, 2:3], field=FIELD, te=te1)
+
+    t_wr = float(np.median(event_times(c1_wrappers, 50, warm=5)))
+    tab1 = torch.empty((1, L.TAB_FLOATS), device=device)
+    sig1, rho1 = torch.empty_like(acqs1), torch.empty((1, 2, H, W, 2), device=device)
+    te1f, pm_row = te1[:, :, 0].contiguous(), maps1[:, 2:3].contiguous()
+
+    def c1_abi():
+        st = torch.cuda.current_stream().cuda_stream
+        L.check(lib.ig_gen_tables(te1f.data_ptr(), 1, NE, FIELD, tab1.data_ptr(), st), "ig_gen_tables")
+        L.check(lib.ig_ideal_fwd(L.MODEL_WFPM, maps1.data_ptr(), 3, tab1.data_ptr(), 1, NE, H * W, R2_SC, 0, sig1.data_ptr(), st), "ig_ideal_fwd")
+        L.check(lib.ig_get_rho_fwd(sig1.data_ptr(), pm_row.data_ptr(), H * W * 2, 0, 0, tab1.data_ptr(), 1, NE, H * W, R2_SC, 0, rho1.data_ptr(), 0, st),
+                "ig_get_rho_fwd")
+
+    out["C1"] = {"what": "IDEAL_Layer forward + get_rho, 1 x 384 x 384 x 6", "latency_us": 1e3 * t_wr,
+                 "graph_latency_us": graph_us(c1_abi), "note": "latency_us: wf.IDEAL_Layer + wf.get_rho through the Python drop-in (table cached); "
+                 "graph_latency_us: ig_gen_tables + ig_ideal_fwd + ig_get_rho_fwd replayed from a CUDA graph",
+                 "voxel_echoes_per_s_graph": None}
+    out["C1"]["voxel_echoes_per_s_graph"] = H * W * NE / (out["C1"]["graph_latency_us"] * 1e-6)
+
+    # ---- C3: TE-augmented forward + solve fwd/bwd, 256 x 192 x 192 x 6, one echo train per sample -------------------------
+    nb3, h3 = 256, 192
+    te3 = synth.te_random(nb3, NE, rng)
+    acqs3, pm3, te3d, maps3 = build_device_inputs(device, 13, nb=nb3, h=h3, w=h3, te=te3)
+    tab3 = ops.gen_tables(te3d, FIELD)
+    nvox3 = nb3 * h3 * h3
+    up_rho = torch.randn((nb3, 2, h3, h3, 2), device=device)
+    t_f = float(np.median(event_times(lambda: ops.ideal_fwd(L.MODEL_WFPM, maps3, tab3, NE, R2_SC), reps)))
+    t_s = float(np.median(event_times(lambda: ops.get_rho_fwd(acqs3, pm3, tab3, R2_SC), reps)))
+    t_b = float(np.median(event_times(lambda: ops.get_rho_bwd(acqs3, pm3, tab3, up_rho, None, R2_SC), reps)))
+    out["C3"] = {"what": "IDEAL_Layer(te per sample) forward, get_rho forward and adjoint, 256 x 192 x 192 x 6 (train-IDEAL-TEaug.py:217,304)",
+                 "forward_ms": t_f, "forward_frac": frac(72, nvox3, t_f), "solve_ms": t_s, "solve_frac": frac(72, nvox3, t_s),
+                 "solve_bwd_ms": t_b, "solve_bwd_frac": frac(128, nvox3, t_b),
+                 "voxel_echoes_per_s": nvox3 * NE / ((t_f + t_s + t_b) * 1e-3)}
+    del acqs3, pm3, maps3, up_rho
+
+    # ---- C4: bipolar mag/phase self-supervised objective (train-IDEAL-single.py:154-157,175) -----------------------------
+    def c4_batch(nb):
+        te = synth.te_random(nb, NE, rng, te_ini_d=0.4e-3, d_te_min=1.0e-3, d_te_d=0.3e-3)
+        g = torch.Generator(device=device)
+        g.manual_seed(17 + nb)
+        m = torch.zeros((nb, 2, H, W, 4), device=device)
+        m[:, 0, :, :, :2] = 0.7 * torch.rand((nb, H, W, 2), device=device, generator=g)
+        m[:, 0, :, :, 2] = torch.rand((nb, H, W), device=device, generator=g)
+        m[:, 1, :, :, :2] = 0.5 * torch.rand((nb, H, W, 2), device=device, generator=g) - 0.25
+        m[:, 1, :, :, 2] = 2.0 * torch.rand((nb, H, W), device=device, generator=g) - 1.0
+        m[:, 1, :, :, 3] = 0.12 * torch.rand((nb, H, W), device=device, generator=g) - 0.06
+        m *= torch.from_numpy(synth.disc_mask(H, W).astype(np.float32)).to(device)[None, None, :, :, None]
+        ted = torch.from_numpy(te).to(device)
+        tab = ops.gen_tables(ted, FIELD)
+        sig = ops.ideal_fwd(L.MODEL_MAGPHA, m, tab, NE, R2_SC)
+        acq = torch.where(sig != 0, sig + 0.02 * torch.randn(sig.shape, device=device, generator=g), torch.zeros_like(sig)).contiguous()
+        return (m * 0.97).contiguous(), acq, ted, tab
+
+    m64, a64, _, tab64 = c4_batch(NB)
+    t64 = float(np.median(event_times(lambda: ops.ideal_loss(L.MODEL_MAGPHA, m64, a64, tab64, R2_SC), reps)))
+    del m64, a64
+    m3, a3, te3s, tab3s = c4_batch(3)
+    g3, l3 = torch.empty_like(m3), torch.empty(1, device=device)
+    scr = ops.loss_scratch(device, 3, H * W)
+    te3f = te3s[:, :, 0].contiguous()
+
+    def c4_abi():
+        st = torch.cuda.current_stream().cuda_stream
+        L.check(lib.ig_gen_tables(te3f.data_ptr(), 3, NE, FIELD, tab3s.data_ptr(), st), "ig_gen_tables")
+        L.check(lib.ig_ideal_loss(L.MODEL_MAGPHA, m3.data_ptr(), 4, a3.data_ptr(), tab3s.data_ptr(), 3, NE, H * W, R2_SC, 0, 1.0 / a3.numel(), g3.data_ptr(), 0,
+                                  l3.data_ptr(), scr.data_ptr(), scr.numel(), st), "ig_ideal_loss")
+
+    us3 = graph_us(c4_abi)
+    out["C4"] = {"what": "IDEAL_mag_Layer(sep_phase) forward + mask + MSE + backward fused (ig_ideal_loss[magpha], bipolar), 384 x 384 x 6",
+                 "nb3_us": us3, "nb3_voxel_echoes_per_s": 3 * H * W * NE / (us3 * 1e-6), "nb64_ms": t64, "nb64_frac": frac(112, NB * H * W, t64),
+                 "nb64_voxel_echoes_per_s": NB * H * W * NE / (t64 * 1e-3),
+                 "note": "nb3: the script's own batch, ig_gen_tables + ig_ideal_loss replayed from a CUDA graph; nb64: roofline batch"}
+    return out
+
+
+def c5_leg(device, rank, world, peak, dist, slices_total, chunk, reps):
+    """C5, gen_LDM_dataset.py:140-254: physics decoding of decoded mag/phase maps into the three clipped images the script writes
+    per slice (and, optionally, the complex signals of its TFRecord), host maps in, host images out.  A sample of the 16 384-slice
+    job is split over the ranks (no collective); the streamed leg uses NUMA-placed pinned buffers and two alternating streams."""
+    from idealgan import _lib as L
+    from idealgan import dist as igdist
+    from idealgan import ops, synth
+    nv = H * W
+    per_rank = max(slices_total // world, chunk)
+    rng = np.random.default_rng(99 + rank)
+    base = synth.magpha_maps(8, H, W, rng, bipolar=False)
+    maps_h = igdist.pinned_empty((per_rank, 2, H, W, 3), device)
+    for k in range(0, per_rank, 8):
+        n = min(8, per_rank - k)
+        maps_h[k:k + n].copy_(torch.from_numpy(base[:n]))
+    te = synth.te_orig(per_rank, NE)
+    images = {"mag": igdist.pinned_empty((per_rank, NE, H, W), device), "pdff": igdist.pinned_empty((per_rank, H, W), device),
+              "r2s": igdist.pinned_empty((per_rank, H, W), device)}
+    # device-resident kernel figure (images only: 24 B read + 24 + 4 + 4 written per voxel; with the complex signals + 48)
+    nbk = min(NB, per_rank)
+    m_dev = maps_h[:nbk].to(device)
+    tab = ops.gen_tables(torch.from_numpy(te[:nbk]).to(device), FIELD)
+    t_img = float(np.median(event_times(lambda: ops.ideal_decode(L.MODEL_MAGPHA, m_dev, tab, NE, R2_SC), reps)))
+    t_all = float(np.median(event_times(lambda: ops.ideal_decode(L.MODEL_MAGPHA, m_dev, tab, NE, R2_SC, want_shat=True), reps)))
+    del m_dev
+
+    decoder = igdist.HostDecoder(L.MODEL_MAGPHA, 3, chunk, NE, nv, want_signals=False, device=device)
+
+    def run():
+        igdist.synthesize_to_host(L.MODEL_MAGPHA, maps_h, te, out_host=False, field=FIELD, r2_sc=R2_SC, chunk_nb=chunk, device=device, images=images,
+                                  decoder=decoder)
+
+    run()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    run()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - w0
+    t = torch.tensor([dt], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    decoder.close()
+    total = per_rank * world
+    return {"what": "IDEAL_mag_Layer on (nb,2,H,W,3) decoder maps -> clip(|S_e|), clip(PDFF), clip(R2*) (gen_LDM_dataset.py:156-158,216-237), "
+                    f"host maps in / host images out, {total} of the 16384 slices split over {world} rank(s)",
+            "slices": total, "slices_per_rank": per_rank, "seconds": dt, "G_voxel_echoes_s": total * nv * NE / dt / 1e9,
+            "bytes_h2d": total * nv * 24, "bytes_d2h": total * nv * 32,
+            "bytes_d2h_before_epilogue": total * nv * 48, "full_job_seconds_at_this_rate": 16384 / total * dt,
+            "kernel": {"images_ms": t_img, "images_frac": 56 * nbk * nv / (t_img * 1e-3) / 1e9 / peak,
+                       "images_and_signals_ms": t_all, "images_and_signals_frac": 104 * nbk * nv / (t_all * 1e-3) / 1e9 / peak, "slices": nbk},
+            "GBps_h2d_plus_d2h_per_rank": per_rank * nv * 56 / dt / 1e9,
+            "api": f"ig_decode_host (3-slot H2D / ig_gen_tables + ig_ideal_decode / D2H pipeline, chunks of {chunk} slices), pinned NUMA-placed buffers"}
+
+
+def copy_ceiling(device, dist, bytes_in, bytes_out):
+    """Bare cudaMemcpyAsync loops (ig_copy_probe) with the step's own byte counts, all ranks at once: what any host-buffer
+    pipeline could reach on this host.  Returns this rank's rates and the seconds its step's input copy needs at that rate."""
+    from idealgan import _lib as L
+    from idealgan import dist as igdist
+    lib = L.load()
+    n_in, n_out = bytes_in // 4, bytes_out // 4
+    h_in, h_out = igdist.pinned_empty((n_in,), device), igdist.pinned_empty((n_out,), device)
+    d_in, d_out = torch.empty(n_in, device=device), torch.empty(n_out, device=device)
+    sec = ctypes.c_double()
+    res = {}
+    for name, direction, reps in (("h2d", 0, 6), ("d2h", 1, 6)):
+        if dist is not None:
+            dist.barrier()
+        h, d, nbytes = (h_in, d_in, bytes_in) if direction == 0 else (h_out, d_out, bytes_out)
+        L.check(lib.ig_copy_probe(h.data_ptr(), d.data_ptr(), 0, 0, nbytes, reps, direction, ctypes.byref(sec)), "ig_copy_probe")
+        res[name + "_gbs"] = nbytes * reps / sec.value / 1e9
+    res["step_copy_seconds"] = bytes_in / (res["h2d_gbs"] * 1e9)      # host -> device dominates the step (528 MB in, 75 MB out, separate engines)
+    return res
 
 
 def run_ours(args):
@@ -217,7 +504,7 @@ def run_ours(args):
     lib = L.load()
     assert lib.ig_device_ok() == 1, "libidealgan targets sm_100 (B200)"
 
-    acqs, pm, te = build_device_inputs(device, 1234 + rank)
+    acqs, pm, te, _ = build_device_inputs(device, 1234 + rank)
     nv = H * W
     inv_n = 1.0 / (acqs.numel() * world)                 # mean over the GLOBAL batch; shards sum to it
     stream = torch.cuda.current_stream()
@@ -244,7 +531,7 @@ def run_ours(args):
     tab_free = [None, None]
     counter = [0]
 
-    def step(ev=None):
+    def step(ev=None, a=acqs, p=pm):
         j = counter[0] % 2
         counter[0] += 1
         loss = reducer.acquire()
@@ -256,12 +543,12 @@ def run_ours(args):
         if ev:
             ev[0].record(stream)
         if peer is not None:
-            L.check(lib.ig_a2a_loss_peer(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
+            L.check(lib.ig_a2a_loss_peer(a.data_ptr(), p.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
                                          loss_local.data_ptr(), scratch.data_ptr(), scratch.numel(), peer.handle, peer.step, peer.lag, peer.prev.data_ptr(),
                                          stream.cuda_stream), "ig_a2a_loss_peer")
             peer.step += 1
         else:
-            L.check(lib.ig_a2a_loss(acqs.data_ptr(), pm.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
+            L.check(lib.ig_a2a_loss(a.data_ptr(), p.data_ptr(), nv * 2, tabs[j].data_ptr(), NB, NE, nv, R2_SC, inv_n, g_pm.data_ptr(), 0, 0,
                                     loss.data_ptr(), scratch.data_ptr(), scratch.numel(), stream.cuda_stream), "ig_a2a_loss")
         if ev:
             ev[1].record(stream)
@@ -295,16 +582,31 @@ def run_ours(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     final_loss = (peer._last if peer is not None else reducer.last()).item()
 
+    # ---- the same kernel on an unmasked batch (no background voxels to skip): rank 0 at N = 1 only -------------------------
+    kernel_ms_unmasked = None
+    if world == 1 and not args.headline_only:
+        a_u, p_u, _, _ = build_device_inputs(device, 4321, masked=False)
+        for _ in range(3):
+            step(None, a_u, p_u)
+        torch.cuda.synchronize()
+        kev_u = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+        with clocks:
+            for e in kev_u:
+                step(e, a_u, p_u)
+            torch.cuda.synchronize()
+        kernel_ms_unmasked = float(np.mean([a.elapsed_time(b) for a, b in kev_u]))
+        del a_u, p_u
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------------------
-    e2e_s, e2e_steps, e2e_loss, h2d, d2h = 0.0, 0, None, 0, 0
+    e2e_s, e2e_steps, e2e_loss, h2d, d2h, ceiling = 0.0, 0, None, 0, 0, None
     if not args.no_e2e:
-        acqs_h = torch.empty(acqs.shape, dtype=torch.float32).pin_memory()
-        pm_h = torch.empty(pm.shape, dtype=torch.float32).pin_memory()
-        te_h = te2.cpu().pin_memory()
+        # pinned buffers from ig_host_alloc: on the GPU's NUMA node where the host has more than one
+        acqs_h, pm_h = igdist.pinned_empty(acqs.shape, device), igdist.pinned_empty(pm.shape, device)
+        te_h = igdist.pinned_empty(te2.shape, device)
+        te_h.copy_(te2)
         acqs_h.copy_(acqs)
         pm_h.copy_(pm)
-        g_h = torch.empty(g_pm.shape, dtype=torch.float32).pin_memory()
-        l_h = torch.empty(1, dtype=torch.float32).pin_memory()
+        g_h, l_h = igdist.pinned_empty(g_pm.shape, device), igdist.pinned_empty((1,), device)
         h2d, d2h = int((acqs_h.numel() + pm_h.numel() + te_h.numel()) * 4), int((g_h.numel() + 1) * 4)
         ctx = ctypes.c_void_p()
         L.check(lib.ig_ctx_create(local, args.chunk, NE, nv, ctypes.byref(ctx)), "ig_ctx_create")
@@ -325,70 +627,110 @@ def run_ours(args):
             e2e_s = time.perf_counter() - w0
         lib.ig_ctx_destroy(ctx)
         e2e_loss = l_h.item() * world if world > 1 else l_h.item()
+        fence()
+        ceiling = copy_ceiling(device, dist, h2d, d2h)
+        ceiling["numa_node"] = lib.ig_host_numa_node(local)
+        del acqs_h, pm_h, g_h
     clocks.close()
 
-    # ---- max over ranks ----------------------------------------------------------------------------------
-    times = torch.tensor([ms, kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    # ---- max / min over ranks ----------------------------------------------------------------------------------
+    times = torch.tensor([ms, kernel_ms, e2e_s * 1e3, -kernel_ms] + ([ceiling["step_copy_seconds"] * 1e3, -ceiling["h2d_gbs"]] if ceiling else [0.0, 0.0]),
+                         dtype=torch.float64, device=device)
+    sums = torch.tensor([ceiling["h2d_gbs"], ceiling["d2h_gbs"]] if ceiling else [0.0, 0.0], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, kernel_ms, e2e_ms = (float(x) for x in times.cpu())
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms, kernel_ms_max, e2e_ms, neg_kmin, copy_ms, neg_h2d_min = (float(x) for x in times.cpu())
     units_per_step = NB * nv * NE * world
     value = units_per_step * args.steps / (ms * 1e-3)
     e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+
+    c5 = None
+    if not args.headline_only:
+        torch.cuda.empty_cache()
+        c5 = c5_leg(device, rank, world, peak, dist, args.c5_slices, args.c5_chunk, 10)
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
         achieved = ALGO_BYTES_PER_VOXEL * NB * nv / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("a2a_loss_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
+            traffic, traffic_src = tj.get("a2a_loss_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
-        cpu_baseline = None
+        cpu_baseline, dropin, configs = None, None, None
+        if world == 1 and not args.headline_only:
+            dropin = dropin_leg(acqs, pm, te, 15)
+            del acqs, pm
+            torch.cuda.empty_cache()
+            configs = configs_leg(device, peak, 15)
+        if configs is None:
+            configs = {}
+        if c5 is not None:
+            configs["C5"] = c5
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
+            arm = CpuArm()
             nbc = 8
-            a_c, p_c, t_c = cpu_sample(nbc)
-            cpu_port_step(a_c, p_c, t_c)
+            x = arm.prepare(*cpu_sample(nbc))
+            arm.step(*x)
             best = float("inf")
             reps = 0
             t_budget = time.perf_counter()
             while reps < 5 and (time.perf_counter() - t_budget) < 25.0:
                 c0 = time.perf_counter()
-                cpu_port_step(a_c, p_c, t_c)
+                arm.step(*x)
                 best = min(best, time.perf_counter() - c0)
                 reps += 1
-            cpu_baseline = {"value": nbc * nv * NE / best, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{nbc} of the {NB} slices ({H}x{W}x{NE}), best of {reps}: reference algorithm as torch-CPU "
-                                      "complex64 op chain + autograd (oracle/ideal_oracle.py); TensorFlow itself is not installable here"}
+            cpu_baseline = {"value": nbc * nv * NE / best, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                            "sample": arm.describe(nbc) + f", best of {reps}"}
+        e2e = None
+        if e2e_steps:
+            e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                   "ms_per_step": e2e_ms / e2e_steps,
+                   "timer": "host perf_counter around the blocking C-ABI call, device synchronised on both sides",
+                   "api": f"ig_a2a_loss_host (3-slot H2D/compute/D2H pipeline, chunks of {args.chunk} slices), buffers from ig_host_alloc "
+                          f"(pinned, NUMA node {ceiling['numa_node']} of the GPU; -1 = the host exposes one node)",
+                   "h2d_gbs_achieved_per_rank": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                   "host_ceiling": {"what": "bare cudaMemcpyAsync loops (ig_copy_probe) of the step's own byte counts, every rank at once",
+                                    "h2d_gbs_sum_over_ranks": float(sums[0]), "d2h_gbs_sum_over_ranks": float(sums[1]),
+                                    "h2d_gbs_slowest_rank": -neg_h2d_min, "step_h2d_ms_slowest_rank": copy_ms,
+                                    "value_at_ceiling": units_per_step / (copy_ms * 1e-3)},
+                   "host_ceiling_gbs": float(sums[0]), "frac_of_host_ceiling": e2e_value / (units_per_step / (copy_ms * 1e-3))}
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "traffic_source": traffic_src or "static: one ncu --set full capture, see profiles/",
+                    "kernel": "a2a_loss_tma_kernel<NE=6, MINB=2, STAGES=3, EXACT, CH=8, MODE=1>", "kernel_ms": kernel_ms,
+                    "kernel_ms_min_over_ranks": -neg_kmin, "kernel_ms_max_over_ranks": kernel_ms_max,
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VOXEL * NB * nv,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured torch copy bandwidth: a lower bound of the HBM rate, some kernels exceed it)"
+                    if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"}
+        if kernel_ms_unmasked is not None:
+            roofline["kernel_ms_unmasked"] = kernel_ms_unmasked
+            roofline["frac_unmasked"] = ALGO_BYTES_PER_VOXEL * NB * nv / (kernel_ms_unmasked * 1e-3) / 1e9 / peak
+            roofline["unmasked_note"] = "same kernel, same shapes, no background voxels (every chunk does the full math)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": NB * world, "sharding": f"batch axis, {NB} slices per GPU, "
-                       + ("scalar loss exchanged by the loss kernel itself (peer-memory stores over NVLink, no collective kernel)" if peer is not None
+                       + (f"scalar loss exchanged by the loss kernel itself (peer-memory stores over NVLink, no collective kernel, lag {args.lag})" if peer is not None
                           else "async NCCL all-reduce of the scalar loss only (overlaps the next step)") if world > 1 else "single GPU",
-                       "l2": f"inputs {(acqs.numel() + pm.numel()) * 4 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
+                       "l2": f"inputs {(NB * NE * nv * 2 + NB * nv * 2) * 4 / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
                        "step": "ig_gen_tables (side stream, double-buffered) + ig_a2a_loss (fused loss + gradient)" + ((" with the scalar exchange fused in (ig_a2a_loss_peer)" if peer is not None else " + async all_reduce(loss)") if world > 1 else ""),
                        "loss": final_loss, "e2e_loss": e2e_loss, **({"exchange_note": exchange_note} if exchange_note else {})},
             "clocks": clocks.summary(),
-            "e2e": None if not e2e_steps else {
-                    "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "timer": "host perf_counter around the blocking C-ABI call, device synchronised on both sides",
-                    "api": f"ig_a2a_loss_host (3-slot H2D/compute/D2H pipeline, chunks of {args.chunk} slices)"},
-            "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "a2a_loss_tma_kernel<NE=6, MINB=2, STAGES=3, EXACT, CH=8, MODE=1>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VOXEL * NB * nv,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"},
+            "e2e": e2e,
+            "gpu_launches": 2 * args.steps + (1 if peer is not None else 0),
+            "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "dropin": dropin,
+            "configs": configs,
         }
         emit(line)
     if dist is not None:
@@ -405,7 +747,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=8, help="slices per chunk of the host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer", help="multi-GPU scalar exchange (see idealgan/dist.py)")
-    ap.add_argument("--lag", type=int, default=1, help="peer exchange: the global loss a step receives is `lag` steps old")
+    ap.add_argument("--lag", type=int, default=2, help="peer exchange: the global loss a step receives is `lag` steps old (2: no rank waits for a peer less than a step behind)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the dropin / unmasked / configs legs (profiling runs)")
+    ap.add_argument("--c5-slices", type=int, default=512, help="C5 leg: slices of the 16384-slice job processed in total (split over the ranks)")
+    ap.add_argument("--c5-chunk", type=int, default=32, help="C5 leg: slices per streamed chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (profiling runs)")
     args = ap.parse_args()

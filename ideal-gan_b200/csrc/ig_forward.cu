@@ -14,7 +14,7 @@
 
 namespace ig {
 
-enum { MODE_FWD = 0, MODE_BWD = 1, MODE_LOSS = 2 };
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_LOSS = 2, MODE_DEC = 3 };
 
 struct FwdParams {
     const float *maps;
@@ -25,9 +25,52 @@ struct FwdParams {
     float *gmaps;
     float *loss;
     void *scratch;
+    float *mag, *pdff, *r2s;   // MODE_DEC: (nb, ne, nv) |S_e|, (nb, nv) PDFF, (nb, nv) R2* map -- each optional, clipped to [0, 1]
     int rows_or_ch, nb, ne, nv, flags;
     float r2_sc, inv_n;
 };
+
+// clip_by_value(x, 0, 1) with TensorFlow's NaN propagation (tf.maximum / tf.minimum return NaN for a NaN operand; fmaxf would not)
+__device__ __forceinline__ float clip01(float x) { return x != x ? x : fminf(fmaxf(x, 0.f), 1.f); }
+__device__ __forceinline__ pk clip01(pk x) { return mk(clip01(x.d.x), clip01(x.d.y)); }
+__device__ __forceinline__ float vdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ pk vdiv(pk a, pk b) { return mk(__fdiv_rn(a.d.x, b.d.x), __fdiv_rn(a.d.y, b.d.y)); }
+
+// Dataset synthesis consumer (gen_LDM_dataset.py:156-158,217-235): the forward model and, in the same pass over the registers,
+// the three images the script writes per slice -- PDFF = |F| / (|W| + |F|), the R2* map and one magnitude image per echo, each
+// clipped to [0, 1].  |S_e| = e^{-te R} |rho_W + c_e rho_F|: when the complex signals are not wanted the field-map phasor (two
+// MUFU + the phase arithmetic per echo) is never formed.
+template <int NE, typename V, int MODEL>
+__device__ __forceinline__ void decode_outputs(const FwdParams &p, const SampleTab<NE> &T, const Voxel<V> &x, int b, int v0) {
+    const int nv = p.nv, ne = p.ne;
+    const bool clip = !(p.flags & IG_F_NO_CLIP);
+    if (p.pdff) {
+        const V mw = vsqrt(vfma(x.rhoW.re, x.rhoW.re, vmul(x.rhoW.im, x.rhoW.im)));
+        const V mf = vsqrt(vfma(x.rhoF.re, x.rhoF.re, vmul(x.rhoF.im, x.rhoF.im)));
+        // the script divides the decoder's magnitude channels as they are (Z2B[i,0,:,:,1] / (Z2B[i,0,:,:,0] + Z2B[i,0,:,:,1])); the
+        // complex-row models have no such channels and use |F| / (|W| + |F|).  0 / 0 = NaN on background, as in the script.
+        const V q = (MODEL == IG_MODEL_MAGPHA) ? vdiv(x.pd, vadd(x.ff, x.pd)) : vdiv(mf, vadd(mw, mf));
+        st_real(p.pdff + static_cast<size_t>(b) * nv, v0, clip ? clip01(q) : q);
+    }
+    if (p.r2s) st_real(p.r2s + static_cast<size_t>(b) * nv, v0, clip ? clip01(x.r2raw) : x.r2raw);
+    if (!p.out && !p.mag) return;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const V d = fast_ex2(vmul(T.r[e].kdec, x.r2));
+            const cx<V> yhat = caffine(x.rhoW, T.r[e].c_re, T.r[e].c_im, x.rhoF);
+            if (p.out) {
+                V c, s;
+                unit_phasor(vfma(T.r[e].sgn, x.bturn, vmul(T.r[e].kphi, x.phi_t)), c, s);
+                st_cx(p.out + static_cast<size_t>(b) * ne * nv * 2 + static_cast<size_t>(e) * nv * 2, v0, cmulv(cx<V>{vmul(d, c), vmul(d, s)}, yhat));
+            }
+            if (p.mag) {
+                const V m = vmul(d, vsqrt(vfma(yhat.re, yhat.re, vmul(yhat.im, yhat.im))));
+                st_real(p.mag + (static_cast<size_t>(b) * ne + e) * nv, v0, clip ? clip01(m) : m);
+            }
+        }
+    }
+}
 
 // one thread's voxels of sample b starting at v0: decode, all echoes, write-out; returns the thread's loss partial
 template <int NE, typename V, int MODEL, int MODE>
@@ -37,6 +80,10 @@ __device__ __forceinline__ float ideal_voxels(const FwdParams &p, const SampleTa
                                                         : static_cast<size_t>(p.rows_or_ch) * nv * 2;
     const Voxel<V> x = decode<V, MODEL>(p.maps + b * map_elems, p.rows_or_ch, nv, v0, p.flags);
     const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+    if constexpr (MODE == MODE_DEC) {
+        decode_outputs<NE, V, MODEL>(p, T, x, b, v0);
+        return 0.f;
+    }
     Adj<V> a;
     a.sg = czero<V>(); a.sgc = czero<V>(); a.tq = czero<V>(); a.q = czero<V>(); a.bq = splat<V>(0.f);
     V lsum = splat<V>(0.f);
@@ -203,7 +250,9 @@ template <typename K> static int resident_grid(K kernel, int nb, int nv, int vpt
 }
 
 template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaStream_t st) {
-    bool packed = (p.nv % 2 == 0) && aligned16(p.maps) && (MODE == MODE_FWD ? aligned16(p.out) : aligned16(p.gmaps));
+    bool packed = (p.nv % 2 == 0) && aligned16(p.maps);
+    if (MODE == MODE_DEC) packed = packed && (!p.out || aligned16(p.out)) && (!p.mag || aligned16(p.mag)) && (!p.pdff || aligned16(p.pdff)) && (!p.r2s || aligned16(p.r2s));
+    else packed = packed && (MODE == MODE_FWD ? aligned16(p.out) : aligned16(p.gmaps));
     if (MODE == MODE_BWD) packed = packed && aligned16(p.gout);
     if (MODE == MODE_LOSS) packed = packed && aligned16(p.acqs) && (!p.out || aligned16(p.out));
     if (MODEL == IG_MODEL_MAGPHA && p.rows_or_ch == 4) {     // 4-channel rows are read/written as float4 in both paths
@@ -268,7 +317,7 @@ template <int MODE> static int launch_model(int model, const FwdParams &p, cudaS
 static int check_model_args(const char *fn, int model, int rows_or_ch, int nb, int ne, int nv) {
     IG_REQUIRE(nb > 0 && nv > 0 && nb <= 65535, IG_E_ARG, "%s: nb=%d (1..65535), nv=%d", fn, nb, nv);
     IG_REQUIRE(ne >= 1 && ne <= IG_MAX_NE, IG_E_NE, "%s: ne=%d outside [1, %d]", fn, ne, IG_MAX_NE);
-    const bool ok = (model == IG_MODEL_WFPM && (rows_or_ch == 3 || rows_or_ch == 4)) || (model == IG_MODEL_FFPD && rows_or_ch == 3) ||
+    const bool ok = (model == IG_MODEL_WFPM && rows_or_ch >= 3) || (model == IG_MODEL_FFPD && rows_or_ch == 3) ||
                     (model == IG_MODEL_MAGPHA && (rows_or_ch == 3 || rows_or_ch == 4));
     IG_REQUIRE(ok, IG_E_ARG, "%s: model %d does not take rows/channels = %d", fn, model, rows_or_ch);
     return 0;
@@ -285,6 +334,18 @@ extern "C" int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, cons
     FwdParams p{};
     p.maps = maps_d; p.tab = tab_d; p.out = out_d; p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv; p.flags = flags; p.r2_sc = r2_sc;
     return launch_model<MODE_FWD>(model, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ig_ideal_decode(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv, float r2_sc,
+                               int flags, float *shat_d, float *mag_d, float *pdff_d, float *r2s_d, void *stream) {
+    IG_REQUIRE(maps_d && tab_d, IG_E_ARG, "ig_ideal_decode: null pointer");
+    IG_REQUIRE(shat_d || mag_d || pdff_d || r2s_d, IG_E_ARG, "ig_ideal_decode: no output requested");
+    if (int rc = check_model_args("ig_ideal_decode", model, rows_or_ch, nb, ne, nv)) return rc;
+    IG_REQUIRE(!(flags & IG_F_FLAT), IG_E_UNSUPPORTED, "ig_ideal_decode: planar outputs only");
+    FwdParams p{};
+    p.maps = maps_d; p.tab = tab_d; p.out = shat_d; p.mag = mag_d; p.pdff = pdff_d; p.r2s = r2s_d; p.rows_or_ch = rows_or_ch; p.nb = nb;
+    p.ne = ne; p.nv = nv; p.flags = flags; p.r2_sc = r2_sc;
+    return launch_model<MODE_DEC>(model, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ig_ideal_bwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv, float r2_sc,

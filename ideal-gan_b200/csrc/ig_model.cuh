@@ -14,7 +14,7 @@ template <typename V> struct Voxel {
     V bturn;            // bipolar phase in turns
     // model-specific leftovers needed by the adjoint
     cx<V> uW, uF;       // unit phasors of the species phases (FFPD: uW = common phasor)
-    V ff, pd;           // FFPD
+    V ff, pd;           // FFPD; MAGPHA: the raw |W|, |F| map values
 };
 
 template <typename V> __device__ __forceinline__ cx<V> ld_row(const float *maps_b, int row, int nv, int v0) {
@@ -69,6 +69,8 @@ template <typename V, int MODEL> __device__ __forceinline__ Voxel<V> decode(cons
             lane_set(pW, l, b0); lane_set(pF, l, b1); lane_set(x.phi_t, l, b2); lane_set(x.bturn, l, 2.0f * b3);
         }
         x.r2raw = x.r2;
+        x.ff = magW;                                     // raw (signed) magnitudes: the PDFF image of ig_ideal_decode divides these
+        x.pd = magF;
         unit_phasor(vmul(2.0f, pW), x.uW.re, x.uW.im);
         unit_phasor(vmul(2.0f, pF), x.uF.re, x.uF.im);
         x.rhoW = cscale(vmul(kRhoSc, magW), x.uW);
@@ -98,6 +100,7 @@ __device__ __forceinline__ void write_grads(float *g_b, int rows_or_ch, int nv, 
         st_row<V>(g_b, 0, nv, v0, cx<V>{vmul(kRhoSc * scale, a.sg.re), vmul(kRhoSc * scale, a.sg.im)});
         st_row<V>(g_b, 1, nv, v0, cx<V>{vmul(kRhoSc * scale, a.sgc.re), vmul(kRhoSc * scale, a.sgc.im)});
         st_row<V>(g_b, 2, nv, v0, cx<V>{gphi, gr2});
+        for (int r = 3; r < rows_or_ch - 1; ++r) st_row<V>(g_b, r, nv, v0, cx<V>{zero, zero});      // rows the model never reads (IDEAL_model.py:246 takes the LAST row)
         if (rows_or_ch > 3) st_row<V>(g_b, rows_or_ch - 1, nv, v0, cx<V>{vmul(-0.5f * kTwoPi * scale, a.bq), zero});
     } else if constexpr (MODEL == IG_MODEL_FFPD) {
         // Re(u0 conj(z)) = u.re z.re + u.im z.im with z = sg / sgc

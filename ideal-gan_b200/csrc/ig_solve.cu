@@ -155,7 +155,7 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
 }
 
 // =================================================================================================
-// get_rho backward (unconstrained solve).  With gy_e = sum_s conj(M^+[s,e]) g_rho_s / rho_sc + g_demod_e:
+// get_rho backward.  With gy_e = sum_s conj(M^+[s,e]) g_rho_s / rho_sc + g_demod_e:
 //   dL/dS_e = conj(Wm_e) gy_e ;  X = sum_e te_e conj(gy_e) y_e ;  B = sum_e s_e Im(conj(gy_e) y_e)
 //   dL/dphi~ = 2 pi fm_sc Im X ;  dL/dR~ = r2_sc Re X ;  dL/db~ = pi B
 // =================================================================================================
@@ -190,6 +190,35 @@ template <int NE, typename V, bool FLAT> __global__ void __launch_bounds__(kThre
         }
         gw = cx<V>{vmul(inv, gw.re), vmul(inv, gw.im)};
         gf = cx<V>{vmul(inv, gf.re), vmul(inv, gf.im)};
+    }
+    if (p.flags & IG_F_PHASE_CONSTRAINT) {
+        // Adjoint of rho_s <- Re(rho_s e^{-i theta}) e^{i theta}, theta = 0.5 arg(z), z = rho_W^2 + rho_F^2 (IDEAL_model.py:584-592): the
+        // upstream on the constrained estimate is carried back onto the unconstrained one, then the plain adjoint below applies.
+        //   a_s = Re(conj(G_s) u), b_s = -Im(conj(G_s) u), m_s = Re(rho_s conj(u)), n_s = Im(rho_s conj(u)),  u = e^{i theta}
+        //   G_s <- a_s u + (sum_s a_s n_s + b_s m_s) / |z|^2 . i z conj(rho_s)          (0 for the second term where z = 0)
+        cx<V> rw = czero<V>(), rf = czero<V>();
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const cx<V> y = demod(modulator(T, e, phi_t, r2, bturn), S[e]);
+                cmac(rw, T.r[e].pw_re, T.r[e].pw_im, y);
+                cmac(rf, T.r[e].pf_re, T.r[e].pf_im, y);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < lanes<V>::n; ++l) {
+            const float wr = lane_get(rw.re, l), wi = lane_get(rw.im, l), fr = lane_get(rf.re, l), fi = lane_get(rf.im, l);
+            const float gwr = lane_get(gw.re, l), gwi = lane_get(gw.im, l), gfr = lane_get(gf.re, l), gfi = lane_get(gf.im, l);
+            const float zr = wr * wr - wi * wi + fr * fr - fi * fi, zi = 2.f * (wr * wi + fr * fi);
+            float ct, st;
+            half_angle(zr, zi, ct, st);
+            const float aw = gwr * ct + gwi * st, bw = gwi * ct - gwr * st, mw = wr * ct + wi * st, nw = wi * ct - wr * st;
+            const float af = gfr * ct + gfi * st, bf = gfi * ct - gfr * st, mf = fr * ct + fi * st, nf = fi * ct - fr * st;
+            const float z2 = zr * zr + zi * zi;
+            const float k = z2 > 0.f ? (aw * nw + bw * mw + af * nf + bf * mf) / z2 : 0.f;
+            lane_set(gw.re, l, aw * ct - k * (zi * wr - zr * wi)); lane_set(gw.im, l, aw * st + k * (zr * wr + zi * wi));
+            lane_set(gf.re, l, af * ct - k * (zi * fr - zr * fi)); lane_set(gf.im, l, af * st + k * (zr * fr + zi * fi));
+        }
     }
     cx<V> X = czero<V>();
     V B = splat<V>(0.f);
@@ -1275,7 +1304,6 @@ extern "C" int ig_get_rho_bwd(const float *acqs_d, const float *pm_d, long pm_bs
                               const float *g_demod_d, float *g_acqs_d, float *g_pm_d, float *g_bip_d, void *stream) {
     IG_REQUIRE(acqs_d && pm_d && tab_d && g_pm_d, IG_E_ARG, "ig_get_rho_bwd: null pointer");
     if (int rc = check_common("ig_get_rho_bwd", nb, ne, nv, 2)) return rc;
-    IG_REQUIRE(!(flags & IG_F_PHASE_CONSTRAINT), IG_E_UNSUPPORTED, "ig_get_rho_bwd: phase-constrained solve has no adjoint kernel");
     const bool flat = flags & IG_F_FLAT;
     IG_REQUIRE(!(flat && (bip_d || g_demod_d || g_bip_d)), IG_E_UNSUPPORTED, "ig_get_rho_bwd: flat layout has no bipolar / demod terms");
     IG_REQUIRE(!flat || !g_rho_d || aligned16(g_rho_d), IG_E_ALIGN, "ig_get_rho_bwd: flat g_rho must be 16-byte aligned");

@@ -29,7 +29,8 @@ def unpack_table(tab, ne):
             "ap": ap, "rec": rec}
 MODEL_WFPM, MODEL_FFPD, MODEL_MAGPHA = 0, 1, 2
 PEER_HANDLE_BYTES = 64
-F_PHASE_CONSTRAINT, F_FLAT, F_ONLY_MAG, F_NO_RELU = 1, 2, 4, 8
+F_PHASE_CONSTRAINT, F_FLAT, F_ONLY_MAG, F_NO_RELU, F_NO_CLIP = 1, 2, 4, 8, 16
+HOST_WRITE_COMBINED = 1
 
 _fp = C.c_void_p          # device / host float pointers travel as integers
 _i, _f, _l, _sz = C.c_int, C.c_float, C.c_long, C.c_size_t
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ig_gen_tables_host": (_i, [_fp, _i, _i, _f, _fp]),
     "ig_loss_scratch_bytes": (_sz, [_i, _i]),
     "ig_ideal_fwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp]),
+    "ig_ideal_decode": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp, _fp, _fp]),
     "ig_ideal_bwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
     "ig_ideal_loss": (_i, [_i, _fp, _i, _fp, _fp, _i, _i, _i, _f, _i, _f, _fp, _fp, _fp, _fp, _sz, _fp]),
     "ig_get_rho_fwd": (_i, [_fp, _fp, _l, _fp, _l, _fp, _i, _i, _i, _f, _i, _fp, _fp, _fp]),
@@ -79,6 +81,13 @@ SIGNATURES = {
     "ig_ctx_create": (_i, [_i, _i, _i, _i, C.POINTER(C.c_void_p)]),
     "ig_ctx_destroy": (None, [C.c_void_p]),
     "ig_a2a_loss_host": (_i, [C.c_void_p, _fp, _fp, _fp, _i, _f, _f, _f, _fp, _fp]),
+    "ig_decode_ctx_create": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_void_p)]),
+    "ig_decode_ctx_destroy": (None, [C.c_void_p]),
+    "ig_decode_host": (_i, [C.c_void_p, _fp, _fp, _i, _f, _f, _i, _fp, _fp, _fp, _fp]),
+    "ig_host_alloc": (_i, [_sz, _i, _i, C.POINTER(C.c_void_p)]),
+    "ig_host_free": (_i, [C.c_void_p]),
+    "ig_host_numa_node": (_i, [_i]),
+    "ig_copy_probe": (_i, [_fp, _fp, _fp, _fp, _sz, _i, _i, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -216,13 +216,90 @@ class PeerLossExchange:
             pass
 
 
-def synthesize_to_host(model, maps_host, te, out_host=None, field=1.5, r2_sc=200.0, chunk_nb=256, flags=0, device=None):
+def pinned_empty(shape, device=None, write_combined=False):
+    """Pinned float32 host tensor from ig_host_alloc: placed on the NUMA node of `device` where the host has more than one.
+    write_combined: input staging only (the CPU reads such pages very slowly).  The buffer is released when the tensor's
+    storage is (the storage keeps the numpy array alive, whose finaliser calls ig_host_free)."""
+    import ctypes
+    import weakref
+
+    import numpy as np
+
+    from . import _lib as L
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    n = 1
+    for d in shape:
+        n *= int(d)
+    ptr = ctypes.c_void_p()
+    L.check(L.load().ig_host_alloc(max(n, 1) * 4, index, L.HOST_WRITE_COMBINED if write_combined else 0, ctypes.byref(ptr)), "ig_host_alloc")
+    arr = np.frombuffer((ctypes.c_float * max(n, 1)).from_address(ptr.value), dtype=np.float32, count=n)
+    weakref.finalize(arr, _pinned_release, ptr.value)
+    return torch.from_numpy(arr).reshape(tuple(int(d) for d in shape))
+
+
+def _pinned_release(ptr):
+    from . import _lib as L
+    try:
+        L.load().ig_host_free(ptr)
+    except Exception:      # noqa: BLE001  (interpreter shutdown)
+        pass
+
+
+class HostDecoder:
+    """ig_decode_ctx: three slots of device staging + streams for the streamed physics decoding (config 5).  Create once, run
+    per shard; nothing is allocated while a shard streams."""
+
+    def __init__(self, model, rows_or_ch, chunk_nb, ne, nv, want_signals=True, device=None):
+        import ctypes
+
+        from . import _lib as L
+        self._L = L
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.handle = ctypes.c_void_p()
+        self.want_signals = bool(want_signals)
+        with torch.cuda.device(self.device):
+            L.check(L.load().ig_decode_ctx_create(self.device.index, model, rows_or_ch, chunk_nb, ne, nv, int(want_signals), ctypes.byref(self.handle)),
+                    "ig_decode_ctx_create")
+
+    def run(self, maps_host, te, out_host=None, images=None, field=1.5, r2_sc=200.0, clip=True):
+        L = self._L
+        if not maps_host.is_contiguous():
+            raise ValueError("HostDecoder: maps_host must be contiguous")
+        te = torch.as_tensor(te, dtype=torch.float32)
+        te = (te[:, :, 0] if te.dim() == 3 else te).contiguous()
+        if out_host is not None and not self.want_signals:
+            raise ValueError("HostDecoder: created without staging for the complex signals")
+        ptr = lambda key: images[key].data_ptr() if images is not None and key in images else 0      # noqa: E731
+        with torch.cuda.device(self.device):
+            L.check(L.load().ig_decode_host(self.handle, maps_host.data_ptr(), te.data_ptr(), maps_host.shape[0], float(field), float(r2_sc),
+                                            0 if clip else L.F_NO_CLIP, 0 if out_host is None else out_host.data_ptr(), ptr("mag"), ptr("pdff"),
+                                            ptr("r2s")), "ig_decode_host")
+
+    def close(self):
+        if self.handle:
+            self._L.load().ig_decode_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001
+            pass
+
+
+def synthesize_to_host(model, maps_host, te, out_host=None, field=1.5, r2_sc=200.0, chunk_nb=256, flags=0, device=None, images=None, decoder=None):
     """Physics decoding of a shard that does not fit (or is not wanted) on the device in one piece -- config 5, the PI-VAE / LDM
     dataset synthesis of gen_LDM_dataset.py:140-254, whose 16 384 x 384 x 384 x 6 echoes are 116 GB.  `maps_host` (pinned CPU
     tensor, this rank's shard) is streamed through the forward kernel in chunks of `chunk_nb` samples on two alternating CUDA
     streams, so that the host->device copy of chunk k + 1, the kernel of chunk k and the device->host copy of chunk k - 1 overlap;
     the result lands in `out_host` (pinned; allocated if None).  `te`: (nb, ne[, 1]) echo times of the shard.  No collective:
-    ranks are independent (shard with `shard()` first)."""
+    ranks are independent (shard with `shard()` first).
+
+    images: None -> the complex signals only (returns out_host).  A dict of pinned host tensors {"mag": (nb,ne,H,W), "pdff":
+    (nb,H,W), "r2s": (nb,H,W)} (or True to allocate them) -> the three clipped images gen_LDM_dataset.py:216-237 writes per slice
+    come out of the same kernel pass (ig_ideal_decode); out_host=False then skips the complex signals altogether: 32 instead
+    of 48 bytes per voxel cross the bus.  Returns (out_host | None, images).  decoder: a HostDecoder to reuse across shards
+    (its staging is allocated once); one is created for the call otherwise."""
     from . import _lib as L
     from . import ops
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
@@ -233,22 +310,51 @@ def synthesize_to_host(model, maps_host, te, out_host=None, field=1.5, r2_sc=200
     ne = te.shape[1]
     H, W = maps_host.shape[2], maps_host.shape[3]          # (nb, rows, H, W, ch) for every model
     shape = (nb, H, W, 2 * ne) if flags & L.F_FLAT else (nb, ne, H, W, 2)
-    if out_host is None:
-        out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
-    if tuple(out_host.shape) != shape:
-        raise ValueError(f"out_host must be {shape}, got {tuple(out_host.shape)}")
-    streams = [torch.cuda.Stream(device) for _ in range(2)]
-    keep = [None, None]                                   # device buffers of the chunk in flight on each stream
+    want_sig = out_host is not False
+    if images is not None and flags & L.F_FLAT:
+        raise ValueError("synthesize_to_host: the image outputs come with the planar signal layout")
+    if want_sig:
+        if out_host is None:
+            out_host = pinned_empty(shape, device)
+        if tuple(out_host.shape) != shape:
+            raise ValueError(f"out_host must be {shape}, got {tuple(out_host.shape)}")
+    elif images is None:
+        raise ValueError("synthesize_to_host: nothing to produce (out_host=False and images=None)")
+    if images is True:
+        images = {"mag": pinned_empty((nb, ne, H, W), device), "pdff": pinned_empty((nb, H, W), device), "r2s": pinned_empty((nb, H, W), device)}
+    if images is not None:
+        for k, shp in (("mag", (nb, ne, H, W)), ("pdff", (nb, H, W)), ("r2s", (nb, H, W))):
+            if k in images and tuple(images[k].shape) != shp:
+                raise ValueError(f"images[{k!r}] must be {shp}, got {tuple(images[k].shape)}")
+    if not flags & L.F_FLAT:
+        # planar outputs: the C pipeline (ig_decode_host: three slots of device staging allocated once, no allocation per chunk)
+        own = decoder is None
+        if own:
+            roc = maps_host.shape[4] if model == L.MODEL_MAGPHA else maps_host.shape[1]
+            decoder = HostDecoder(model, roc, min(chunk_nb, nb), ne, H * W, want_sig, device)
+        try:
+            decoder.run(maps_host, te, out_host if want_sig else None, images, field, r2_sc)
+        finally:
+            if own:
+                decoder.close()
+        return out_host if images is None else ((out_host if want_sig else None), images)
+    # channel-interleaved signals (ig_ideal_fwd with IG_F_FLAT): two cached streams, device staging reused across chunks
+    streams = _flat_streams.setdefault(device.index, [torch.cuda.Stream(device) for _ in range(2)])
     te_dev = te.to(device)
+    bufs = [None, None]
     for k, start in enumerate(range(0, nb, chunk_nb)):
         stop = min(start + chunk_nb, nb)
         st = streams[k % 2]
         with torch.cuda.stream(st):
-            m = maps_host[start:stop].to(device, non_blocking=True)
+            if bufs[k % 2] is None:
+                bufs[k % 2] = torch.empty((min(chunk_nb, nb),) + tuple(maps_host.shape[1:]), dtype=torch.float32, device=device)
+            m = bufs[k % 2][: stop - start]
+            m.copy_(maps_host[start:stop], non_blocking=True)
             tab = ops.gen_tables(te_dev[start:stop].contiguous(), field)
-            sig = ops.ideal_fwd(model, m, tab, ne, r2_sc, flags)
-            out_host[start:stop].copy_(sig, non_blocking=True)
-            keep[k % 2] = (m, tab, sig)                   # freed when this stream's next chunk replaces them (stream-ordered allocator)
+            out_host[start:stop].copy_(ops.ideal_fwd(model, m, tab, ne, r2_sc, flags), non_blocking=True)
     for st in streams:
         st.synchronize()
     return out_host
+
+
+_flat_streams = {}

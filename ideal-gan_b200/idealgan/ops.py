@@ -13,7 +13,9 @@ PDFF_MODES = {"complex_sum": 0, "mag_sum": 1, "mag_disc": 2}
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (the raw-handle call: torch.cuda.current_stream() builds a
+    Stream object and costs ~5 us, a fifth of a small launch)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _chk(t, name, ndim=None):
@@ -66,9 +68,9 @@ def _model_dims(model, maps):
             raise ValueError(f"mag/phase maps must be (nb, 2, H, W, 3|4), got {tuple(maps.shape)}")
         return maps, nb, H, W, ch
     nb, rows, H, W, ch = maps.shape
-    ok = rows in (3, 4) if model == L.MODEL_WFPM else rows == 3
+    ok = rows >= 3 if model == L.MODEL_WFPM else rows == 3          # IDEAL_model.py:246: any row count above 3, the LAST row is the bipolar one
     if ch != 2 or not ok:
-        raise ValueError(f"maps for model {model} must be (nb, 3{'|4' if model == L.MODEL_WFPM else ''}, H, W, 2), got {tuple(maps.shape)}")
+        raise ValueError(f"maps for model {model} must be (nb, 3{'+' if model == L.MODEL_WFPM else ''}, H, W, 2), got {tuple(maps.shape)}")
     return maps, nb, H, W, rows
 
 
@@ -79,6 +81,20 @@ def ideal_fwd(model, maps, tab, ne, r2_sc=200.0, flags=0):
     L.check(L.load().ig_ideal_fwd(model, maps.data_ptr(), roc, tab.data_ptr(), nb, ne, H * W, float(r2_sc), flags,
                                   out.data_ptr(), _stream()), "ig_ideal_fwd")
     return out
+
+
+def ideal_decode(model, maps, tab, ne, r2_sc=200.0, want_shat=False, want_mag=True, want_pdff=True, want_r2s=True, clip=True):
+    """Forward model + the images gen_LDM_dataset.py:217-235 writes per slice, one pass: (S_hat (nb,ne,H,W,2) | None,
+    |S_hat| (nb,ne,H,W) | None, PDFF (nb,H,W) | None, R2* map (nb,H,W) | None), the images clipped to [0, 1] unless clip=False."""
+    maps, nb, H, W, roc = _model_dims(model, maps)
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=maps.device)      # noqa: E731
+    shat = new(nb, ne, H, W, 2) if want_shat else None
+    mag = new(nb, ne, H, W) if want_mag else None
+    pdff = new(nb, H, W) if want_pdff else None
+    r2s = new(nb, H, W) if want_r2s else None
+    L.check(L.load().ig_ideal_decode(model, maps.data_ptr(), roc, tab.data_ptr(), nb, ne, H * W, float(r2_sc), 0 if clip else L.F_NO_CLIP,
+                                     _ptr(shat), _ptr(mag), _ptr(pdff), _ptr(r2s), _stream()), "ig_ideal_decode")
+    return shat, mag, pdff, r2s
 
 
 def ideal_bwd(model, maps, tab, ne, gout, r2_sc=200.0, flags=0):

@@ -8,16 +8,63 @@ from . import _lib as L
 from . import ops
 
 
+class _TableCache:
+    """Per-sample tables (gen_M / gen_A constants, ig_gen_tables) keyed on the echo times, so that the operators of one
+    training step -- acq_to_acq, get_rho, acq_uncertainty on the same `te` -- build the table once and no call moves `te`
+    to the host.  Host-resident echo times (numpy / CPU tensors, what gen_TEvar returns) are keyed on their bytes; device
+    tensors on (address, shape, strides, torch's in-place version counter -- shared by every alias of the storage), with a
+    strong reference held while cached so the address cannot be handed to another allocation under the entry."""
+
+    def __init__(self, capacity=16):
+        self.capacity = capacity
+        self.entries = {}            # key -> (table, te reference or None)
+        self.hits = self.misses = 0
+
+    def get(self, te, field, device):
+        stream = torch._C._cuda_getCurrentRawStream(device.index)     # a table is ordered on the stream that built it
+        if te.is_cuda:
+            key = ("dev", te.data_ptr(), te._version, tuple(te.shape), te.stride(), float(field), device.index, stream)
+            hold = te
+        else:
+            key = ("host", te.numpy().tobytes(), tuple(te.shape), float(field), device.index, stream)
+            hold = None
+        hit = self.entries.get(key)
+        if hit is not None:
+            self.hits += 1
+            return hit[0]
+        self.misses += 1
+        tab = ops.gen_tables(te.to(device).contiguous(), field)
+        if len(self.entries) >= self.capacity:
+            self.entries.pop(next(iter(self.entries)))
+        self.entries[key] = (tab, hold)
+        return tab
+
+    def clear(self):
+        self.entries.clear()
+
+
+table_cache = _TableCache()
+
+
 def _tables(te, field, device):
-    """te: (nb, ne[, 1]) tensor/array on any device -> (table on `device`, ne).  No gradient: echo times are data."""
+    """te: (nb, ne[, 1]) tensor/array on any device -> (table on `device`, ne).  No gradient: echo times are data.
+    Device-resident echo times never visit the host (one 5 us ig_gen_tables launch on a cache miss)."""
     if not isinstance(te, torch.Tensor):
         te = torch.as_tensor(te, dtype=torch.float32)
-    te = te.detach().to(device=device, dtype=torch.float32)
-    if te.dim() == 3:
-        te = te[:, :, 0]
-    if te.dim() != 2:
+    te = te.detach()
+    if te.dtype != torch.float32:
+        te = te.to(torch.float32)
+    if te.dim() not in (2, 3) or (te.dim() == 3 and te.shape[2] != 1):
         raise ValueError(f"te must be (nb, ne, 1) or (nb, ne), got {tuple(te.shape)}")
-    return ops.gen_tables(te.contiguous(), field), te.shape[1]
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return table_cache.get(te, field, device), te.shape[1]
+
+
+def _no_grad(*tensors):
+    """True when nothing asks for a gradient: the operator then skips torch.autograd.Function (15-20 us of host time per
+    call, more than a single-slice kernel runs)."""
+    return not torch.is_grad_enabled() or not any(t is not None and t.requires_grad for t in tensors)
 
 
 def _check_batch(te_nb, nb):
@@ -49,7 +96,19 @@ def ideal_forward(model, maps, te, field=1.5, r2_sc=200.0, flags=0):
     result is channel-interleaved, (nb, H, W, 2 ne) = data.A_from_MEBCRN(IDEAL_op(maps)) in one kernel (train-sup.py:242-244)."""
     tab, ne = _tables(te, field, maps.device)
     _check_batch(tab.shape[0], maps.shape[0])
+    if _no_grad(maps):
+        return ops.ideal_fwd(model, maps, tab, ne, float(r2_sc), int(flags))
     return _IdealForward.apply(maps, tab, model, ne, float(r2_sc), int(flags))
+
+
+def ldm_decode(maps, te, field=1.5, r2_sc=200.0, model=None, want_shat=True, clip=True):
+    """Inference-only physics decoding of gen_LDM_dataset.py:156-158,216-237 in one kernel: decoded maps -> (S_hat | None,
+    |S_hat| (nb,ne,H,W), PDFF (nb,H,W), R2* map (nb,H,W)), the three images clipped to [0, 1].  `maps`: the script's
+    (nb,2,H,W,3|4) mag/phase tensor by default; model = L.MODEL_WFPM / L.MODEL_FFPD for the complex-row parameterisations."""
+    tab, ne = _tables(te, field, maps.device)
+    _check_batch(tab.shape[0], maps.shape[0])
+    with torch.no_grad():
+        return ops.ideal_decode(L.MODEL_MAGPHA if model is None else model, maps.detach(), tab, ne, r2_sc, want_shat=want_shat, clip=clip)
 
 
 class _GetRho(torch.autograd.Function):
@@ -68,9 +127,6 @@ class _GetRho(torch.autograd.Function):
     def backward(ctx, g_rho, g_demod):
         acqs, pm, tab = ctx.saved_tensors
         r2_sc, flags = ctx.cfg
-        if flags & L.F_PHASE_CONSTRAINT:
-            raise NotImplementedError("get_rho(phase_constraint=True) is an inference-only operator in the reference's "
-                                      "callers (ROI-analysis.py:217-228); no adjoint kernel is provided")
         g_demod = None if g_demod is None or g_demod.numel() == 0 else g_demod.contiguous()
         g_rho = None if g_rho is None else g_rho.contiguous()
         g_acqs, g_pm = ops.get_rho_bwd(acqs, pm, tab, g_rho, g_demod, r2_sc, flags, need_acqs=ctx.needs_input_grad[0])
@@ -83,7 +139,10 @@ def get_rho(acqs, pm, te, field=1.5, r2_sc=200.0, flags=0, want_demod=False):
     _check_batch(tab.shape[0], acqs.shape[0])
     if ne != (acqs.shape[-1] // 2 if flat else acqs.shape[1]):
         raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[-1] // 2 if flat else acqs.shape[1]}")
-    rho, demod = _GetRho.apply(acqs, pm, tab, float(r2_sc), int(flags), bool(want_demod))
+    if _no_grad(acqs, pm):
+        rho, demod = ops.get_rho_fwd(acqs, pm, tab, float(r2_sc), int(flags), bool(want_demod))
+    else:
+        rho, demod = _GetRho.apply(acqs, pm, tab, float(r2_sc), int(flags), bool(want_demod))
     return (rho, demod) if want_demod else rho
 
 
@@ -111,6 +170,8 @@ def acq_to_acq(acqs, pm, te, field=1.5, r2_sc=200.0, only_mag=False):
     _check_batch(tab.shape[0], acqs.shape[0])
     if ne != acqs.shape[1]:
         raise ValueError(f"te has {ne} echoes, acquisitions have {acqs.shape[1]}")
+    if _no_grad(acqs, pm):
+        return ops.a2a_fwd(acqs, pm, tab, float(r2_sc), L.F_ONLY_MAG if only_mag else 0, want_rho=True)
     return _AcqToAcq.apply(acqs, pm, tab, float(r2_sc), L.F_ONLY_MAG if only_mag else 0)
 
 

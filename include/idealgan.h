@@ -10,7 +10,7 @@
  *  - All tensors are float32, C-contiguous, in the reference's own layouts (data.py:98-137):
  *      acquisitions "MEBCRN"  (nb, ne, nv, 2)      nv = H*W, last axis (Re, Im)
  *      acquisitions "flat"    (nb, nv, 2*ne)       Re/Im interleaved per echo
- *      maps WF-PM             (nb, rows, nv, 2)    rows = 3 | 4 (row 3 = bipolar phase / pi)
+ *      maps WF-PM             (nb, rows, nv, 2)    rows >= 3; rows > 3: the LAST row = bipolar phase / pi (IDEAL_model.py:246-247)
  *      maps ff/pd/phase       (nb, 3, nv, 2)
  *      maps mag/phase         (nb, 2, nv, ch)      ch = 3 | 4 (channel 3 of row 1 = bipolar / 4pi)
  *      PM ("param maps")      row 0 of a (nb, rows>=1, nv, 2) tensor: (phi/300, R2* / r2_sc)
@@ -64,7 +64,8 @@ enum {
     IG_F_PHASE_CONSTRAINT = 1,  /* get_rho(phase_constraint=True)                                 */
     IG_F_FLAT = 2,              /* flat layout (MEBCRN=False)                                     */
     IG_F_ONLY_MAG = 4,          /* acq_to_acq(only_mag=True): second output is |S_hat|, 1 channel  */
-    IG_F_NO_RELU = 8            /* IG_MODEL_WFPM without the relu gate on R2* (not used by wflib) */
+    IG_F_NO_RELU = 8,           /* IG_MODEL_WFPM without the relu gate on R2* (not used by wflib) */
+    IG_F_NO_CLIP = 16           /* ig_ideal_decode: images as computed, without clip_by_value(., 0, 1) */
 };
 
 enum { IG_E_ARG = -1, IG_E_NE = -2, IG_E_ALIGN = -3, IG_E_SCRATCH = -4, IG_E_UNSUPPORTED = -5 };
@@ -90,6 +91,13 @@ size_t ig_loss_scratch_bytes(int nb, int nv);
  * out_d: (nb, ne, nv, 2), or with IG_F_FLAT the channel-interleaved (nb, nv, 2 ne) of data.A_from_MEBCRN (forward only). */
 int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
                  float r2_sc, int flags, float *out_d, void *stream);
+/* The forward model as the dataset-synthesis script consumes it (gen_LDM_dataset.py:156-158,217-235): any of
+ *   shat_d (nb, ne, nv, 2) complex signals (the TFRecord payload), mag_d (nb, ne, nv) = clip(|S_e|, 0, 1) (the multi-echo images),
+ *   pdff_d (nb, nv) = clip(|F| / (|W| + |F|), 0, 1), r2s_d (nb, nv) = clip(R2* map, 0, 1)           (NULL = not wanted)
+ * in ONE pass over the maps; IG_F_NO_CLIP leaves the images unclipped (mag_d is then IDEAL_mag(..)'s only_mag counterpart).
+ * 0/0 on background stays NaN, as tf.clip_by_value leaves it. */
+int ig_ideal_decode(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
+                    float r2_sc, int flags, float *shat_d, float *mag_d, float *pdff_d, float *r2s_d, void *stream);
 /* adjoint: gout_d (nb, ne, nv, 2) upstream -> gmaps_d (same shape as maps, every element written) */
 int ig_ideal_bwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
                  float r2_sc, int flags, const float *gout_d, float *gmaps_d, void *stream);
@@ -242,6 +250,27 @@ void ig_ctx_destroy(ig_ctx *ctx);
 /* acqs_h (nb, ne, nv, 2), pm_h (nb, 1, nv, 2), te_h (nb, ne) -> loss_h[0], g_pm_h (nb, 1, nv, 2).  Blocking. */
 int ig_a2a_loss_host(ig_ctx *ctx, const float *acqs_h, const float *pm_h, const float *te_h, int nb, float field,
                      float r2_sc, float inv_n, float *loss_h, float *g_pm_h);
+
+/* Config 5 (gen_LDM_dataset.py:140-254): a shard of decoder maps streamed through ig_ideal_decode, host buffers on both sides.
+ * The context owns three slots of device staging for chunks of chunk_nb samples (want_shat: also for the complex signals).
+ * maps_h (nb, ...) in the model's layout, te_h (nb, ne) -> any of shat_h (nb,ne,nv,2), mag_h (nb,ne,nv), pdff_h (nb,nv),
+ * r2s_h (nb,nv) (NULL = not wanted; images clipped to [0,1] unless IG_F_NO_CLIP).  Blocking; host buffers should be pinned. */
+typedef struct ig_decode_ctx ig_decode_ctx;
+int ig_decode_ctx_create(int device, int model, int rows_or_ch, int chunk_nb, int ne, int nv, int want_shat, ig_decode_ctx **out);
+void ig_decode_ctx_destroy(ig_decode_ctx *ctx);
+int ig_decode_host(ig_decode_ctx *ctx, const float *maps_h, const float *te_h, int nb, float field, float r2_sc, int flags,
+                   float *shat_h, float *mag_h, float *pdff_h, float *r2s_h);
+
+/* Pinned host memory placed on the NUMA node of `device` (sysfs numa_node of its PCI function; plain cudaHostAlloc where the host
+ * has one node or hides the topology).  IG_HOST_WRITE_COMBINED: write-combined pages -- faster for the GPU to pull, very slow for
+ * the CPU to read back: input staging only.  ig_host_numa_node: the node, or -1. */
+enum { IG_HOST_WRITE_COMBINED = 1 };
+int ig_host_alloc(size_t bytes, int device, int flags, void **out);
+int ig_host_free(void *p);
+int ig_host_numa_node(int device);
+/* Bare cudaMemcpyAsync loop, the ceiling of any host-buffer pipeline on this host: dir 0 host->device, 1 device->host, 2 both at
+ * once (second buffer pair).  seconds_out = wall time of `reps` copies of `bytes` per direction. */
+int ig_copy_probe(void *host, void *dev, void *host2, void *dev2, size_t bytes, int reps, int dir, double *seconds_out);
 
 #ifdef __cplusplus
 }

@@ -509,6 +509,36 @@ def gen_regs():
     save("regs", **out)
 
 
+def gen_ldm():
+    """The per-slice images of gen_LDM_dataset.py:216-218,225-227,234-237 (PDFF, R2*, multi-echo magnitudes, each clipped to
+    [0, 1]): the script's own statements on the shim.  Its forward call `IDEAL_op(Z2B)` cannot run in the reference for the
+    2-row x 3-channel tensor the script builds (IDEAL_mag_Layer() dispatches to IDEAL_mag, and IDEAL_mag_phase
+    needs a 4th channel); the signals are therefore produced by the reference's IDEAL_mag_phase with a zero bipolar channel
+    appended -- the semantics the drop-in gives the 3-channel tensor."""
+    rng = np.random.default_rng(9)
+    src = _reference_script_lines("gen_LDM_dataset.py", [
+        "X1 = tf.squeeze(Z2B[i,0,:,:,1]/(", "X1 = tf.clip_by_value(X1", "X2 = tf.squeeze(Z2B[i,0,:,:,2]", "X2 = tf.clip_by_value(X2",
+        "X3 = tf.math.sqrt(tf.reduce_sum(tf.square(Z2B2A[i,...]),axis=-1))", "X3 = tf.squeeze(X3)", "X3 = tf.clip_by_value(X3"])
+    out = {}
+    nb, ne = 3, 6
+    maps = synth.magpha_maps(nb, H, W, rng, bipolar=False)                      # (nb, 2, H, W, 3), zero outside the disc (0/0 -> NaN PDFF)
+    maps[:, 0, :, :, :2] *= 1.6                                                # some magnitudes and signals above 1: the clip matters
+    maps[0, 0, :3, :, 2] = -0.2                                                # and some R2* below 0
+    te = synth.te_orig(nb, ne)
+    maps4 = np.concatenate([maps, np.zeros_like(maps[..., :1])], axis=-1)
+    with torch.no_grad():
+        sig = wf.IDEAL_mag_Layer(sep_phase=True)(T(maps4), T(te), training=False)
+        pdff, r2s, mags = [], [], []
+        for i in range(nb):
+            ns_ = {"tf": tf_shim, "Z2B": T(maps), "Z2B2A": sig, "i": i}
+            exec(src, ns_)
+            pdff.append(N(ns_["X1"])); r2s.append(N(ns_["X2"])); mags.append(N(ns_["X3"]))
+    out.update({"ldm_maps": maps, "ldm_te": te, "ldm_sig": N(sig), "ldm_pdff": np.stack(pdff), "ldm_r2s": np.stack(r2s),
+                "ldm_mag": np.stack(mags)})
+    assert np.isnan(out["ldm_pdff"]).any() and (out["ldm_mag"] == 1.0).any() and (out["ldm_r2s"] == 0.0).any()
+    save("ldm", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_tables()
@@ -520,3 +550,4 @@ if __name__ == "__main__":
     gen_rician()
     gen_layout()
     gen_regs()
+    gen_ldm()

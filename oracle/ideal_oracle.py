@@ -615,6 +615,18 @@ def roi_maps(maps, var=None, mode=None):
     return torch.cat([out, pv], dim=-1)
 
 
+def ldm_images(out_maps, te=None, field=1.5, rdtype=torch.float32):
+    """gen_LDM_dataset.py:156-158,216-218,225-227,234-237: the decoded mag/phase maps (nb,2,H,W,3|4) -> the forward signals and the
+    three images the script writes per slice, each clip_by_value(., 0, 1) (NaN from 0/0 on background stays NaN):
+    (S_hat (nb,ne,H,W,2), |S_hat| (nb,ne,H,W), PDFF = |F| / (|W| + |F|) on the raw magnitude channels (nb,H,W), R2* map (nb,H,W))."""
+    sig = IDEAL_mag_Layer(field=field)(out_maps, te=te, rdtype=rdtype)
+    m = out_maps.to(rdtype)
+    pdff = torch.clamp(m[:, 0, :, :, 1] / (m[:, 0, :, :, 0] + m[:, 0, :, :, 1]), 0.0, 1.0)
+    r2s = torch.clamp(m[:, 0, :, :, 2], 0.0, 1.0)
+    mag = torch.clamp(torch.sqrt((sig ** 2).sum(-1)), 0.0, 1.0)
+    return sig, mag, pdff, r2s
+
+
 # ----------------------------------------------------------------------------------------------
 # layout adapters (data.py:262-329)
 # ----------------------------------------------------------------------------------------------

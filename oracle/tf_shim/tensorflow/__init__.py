@@ -187,6 +187,11 @@ def pow(x, y):  # noqa: A001
     return _t.pow(x, y)
 
 
+def clip_by_value(t, clip_value_min, clip_value_max, name=None):
+    """tf.clip_by_value = minimum(maximum(t, lo), hi); NaN stays NaN in both libraries."""
+    return _t.clamp(t, clip_value_min, clip_value_max)
+
+
 def reduce_sum(x, axis=None, keepdims=False):
     if axis is None:
         return _t.sum(x)
@@ -213,6 +218,28 @@ def matmul(a, b, transpose_a=False, transpose_b=False, adjoint_a=False, adjoint_
 
 def stop_gradient(x):
     return x.detach()
+
+
+class GradientTape:
+    """`tf.GradientTape` on torch autograd: `watch` marks a leaf, `gradient` differentiates the recorded graph
+    (oracle/tf_ref.py replays the golden fixtures through the same tape code real TensorFlow runs)."""
+
+    def __init__(self, persistent=False, watch_accessed_variables=True):
+        self._persistent = persistent
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def watch(self, x):
+        x.requires_grad_(True)
+
+    def gradient(self, target, sources):
+        single = not isinstance(sources, (list, tuple))
+        grads = _t.autograd.grad(target, [sources] if single else list(sources), allow_unused=True, retain_graph=self._persistent)
+        return grads[0] if single else list(grads)
 
 
 def function(func=None, **kwargs):

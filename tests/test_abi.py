@@ -35,7 +35,9 @@ def test_argument_validation_without_gpu():
     buf = (ctypes.c_float * 16)()
     p = ctypes.addressof(buf)
     assert lib.ig_gen_tables_host(p, 1, 17, 1.5, p) == -2                    # ne > IG_MAX_NE
-    assert lib.ig_ideal_fwd(0, p, 5, p, 1, 6, 16, 200.0, 0, p, 0) == -1      # rows = 5 is no WF-PM tensor
+    assert lib.ig_ideal_fwd(0, p, 2, p, 1, 6, 16, 200.0, 0, p, 0) == -1      # rows = 2 is no WF-PM tensor (>= 3: the last row is the bipolar one)
+    assert lib.ig_ideal_fwd(1, p, 4, p, 1, 6, 16, 200.0, 0, p, 0) == -1      # ff/pd/phase maps have exactly 3 rows
+    assert lib.ig_ideal_decode(2, p, 3, p, 1, 6, 16, 200.0, 0, 0, 0, 0, 0, 0) == -1   # no output requested
     assert lib.ig_a2a_loss(p, p, 0, p, 1, 6, 16, 200.0, 1.0, p, 0, 0, p, p, 8, 0) == -4   # scratch too small
     assert lib.ig_get_rho_fwd(p, p, 0, 0, 0, p, 1, 1, 16, 200.0, 0, p, 0, 0) == -2        # LS solve needs ne >= 2
     # uncertainty objectives: r2_mean without r2_var; too few echoes

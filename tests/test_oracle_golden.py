@@ -319,6 +319,19 @@ def test_roi_maps(golden, rdtype, tol):
     assert_close(mag[..., 4], g["roi_var"][:, 1, :, :, 0], tol)
 
 
+@pytest.mark.parametrize("rdtype,tol", DT)
+def test_ldm_images(golden, rdtype, tol):
+    """The dataset-synthesis images (gen_LDM_dataset.py:216-237) incl. NaN on background and the clip at both ends."""
+    g = golden("ldm")
+    sig, mag, pdff, r2s = orc.ldm_images(tt(g["ldm_maps"], rdtype=rdtype), te=tt(g["ldm_te"], rdtype=rdtype), rdtype=rdtype)
+    assert_close(npy(sig), g["ldm_sig"], tol, "signals")
+    assert_close(npy(mag), g["ldm_mag"], tol, "magnitude images")
+    nan = np.isnan(g["ldm_pdff"])
+    assert nan.any() and np.array_equal(np.isnan(npy(pdff)), nan)
+    assert_close(np.nan_to_num(npy(pdff)), np.nan_to_num(g["ldm_pdff"]), tol, "PDFF")
+    assert_close(npy(r2s), g["ldm_r2s"], 0.0, "R2*")
+
+
 def test_round_trip_and_idempotence():
     """SURVEY §8c KATs (i)-(iv) in fp64."""
     from idealgan import synth

@@ -155,10 +155,9 @@ def test_get_rho_vs_reference_vectors(golden, name):
     rho, dem = ops.get_rho_fwd(a, p, tab, r2, flags, want_demod=True)
     assert_close(host(rho), g[name + "_rho"], TOL, "rho")
     assert_close(host(dem), g[name + "_demod"], TOL, "demod")
-    if not pc:
-        ga, gp = ops.get_rho_bwd(a, p, tab, dev(g[name + "_up_rho"]), dev(g[name + "_up_demod"]), r2)
-        assert_close(host(ga), g[name + "_gacqs"], TOL, "grad acqs")
-        assert_close(host(gp), g[name + "_gpm"], TOL, "grad pm")
+    ga, gp = ops.get_rho_bwd(a, p, tab, dev(g[name + "_up_rho"]), dev(g[name + "_up_demod"]), r2, flags)
+    assert_close(host(ga), g[name + "_gacqs"], TOL, "grad acqs")
+    assert_close(host(gp), g[name + "_gpm"], TOL, "grad pm")
 
 
 def test_get_rho_bipolar_and_flat_vs_reference_vectors(golden):

@@ -80,13 +80,9 @@ def test_get_rho_with_autograd(golden, name):
     assert_close(host(rho), g[name + "_rho"], TOL)
     assert_close(host(dem), g[name + "_demod"], TOL)
     loss = (rho * dev(g[name + "_up_rho"])).sum() + (dem * dev(g[name + "_up_demod"])).sum()
-    if pc:
-        with pytest.raises(NotImplementedError):
-            torch.autograd.grad(loss, [a, p])
-    else:
-        ga, gp = torch.autograd.grad(loss, [a, p])
-        assert_close(host(ga), g[name + "_gacqs"], TOL)
-        assert_close(host(gp), g[name + "_gpm"], TOL)
+    ga, gp = torch.autograd.grad(loss, [a, p])                         # incl. the adjoint of the phase constraint (:584-592)
+    assert_close(host(ga), g[name + "_gacqs"], TOL)
+    assert_close(host(gp), g[name + "_gpm"], TOL)
 
 
 def test_get_rho_default_te_bipolar_and_flat(golden):
