@@ -377,20 +377,28 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) pdff_u
 
 // PDFF extraction (ROI-analysis.py:301-306,344-354; gen_LDM_dataset.py:217-218): mode 0 |F|/|W+F|, 1 |F|/(|W|+|F|),
 // 2 magnitude-discriminated; NaN (0/0) -> 0
-__global__ void pdff_extract_kernel(const float *__restrict__ rho, int nb, int nv, int mode, float *__restrict__ out) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (v >= nv) return;
-    const float2 w = reinterpret_cast<const float2 *>(rho)[(static_cast<size_t>(b) * 2 + 0) * nv + v];
-    const float2 f = reinterpret_cast<const float2 *>(rho)[(static_cast<size_t>(b) * 2 + 1) * nv + v];
-    const float wa = sqrtf(w.x * w.x + w.y * w.y), fa = sqrtf(f.x * f.x + f.y * f.y);
-    float r;
-    if (mode == 1) {
-        r = fa / (wa + fa);
-    } else {
-        const float wf = sqrtf((w.x + f.x) * (w.x + f.x) + (w.y + f.y) * (w.y + f.y));
-        r = (mode == 0 || fa >= wa) ? fa / wf : 1.0f - wa / wf;
+// Two voxels per thread where the shape allows (16-byte streaming loads of both species, one 8-byte store): the one-voxel version
+// moved 20 bytes per thread and reached 54 % of the HBM rate.
+template <typename V> __global__ void __launch_bounds__(kThreads) pdff_extract_kernel(const float *__restrict__ rho, int nb, int nv, int mode, float *__restrict__ out) {
+    const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n, b = blockIdx.y;
+    if (v0 >= nv) return;
+    const float *rho_b = rho + static_cast<size_t>(b) * 2 * nv * 2;
+    const cx<V> w = ld_cx(rho_b, v0, V{}), f = ld_cx(rho_b + static_cast<size_t>(nv) * 2, v0, V{});
+    V res;
+#pragma unroll
+    for (int l = 0; l < lanes<V>::n; ++l) {
+        const float wx = lane_get(w.re, l), wy = lane_get(w.im, l), fx = lane_get(f.re, l), fy = lane_get(f.im, l);
+        const float wa = sqrtf(wx * wx + wy * wy), fa = sqrtf(fx * fx + fy * fy);
+        float r;
+        if (mode == 1) {
+            r = fa / (wa + fa);
+        } else {
+            const float wf = sqrtf((wx + fx) * (wx + fx) + (wy + fy) * (wy + fy));
+            r = (mode == 0 || fa >= wa) ? fa / wf : 1.0f - wa / wf;
+        }
+        lane_set(res, l, (isnan(r) || isinf(r)) ? 0.f : r);
     }
-    out[static_cast<size_t>(b) * nv + v] = (isnan(r) || isinf(r)) ? 0.f : r;
+    st_real(out + static_cast<size_t>(b) * nv, v0, res);
 }
 
 static int check_nv(const char *fn, int nb, int ne, int nv, int min_ne) {
@@ -500,7 +508,10 @@ extern "C" int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const f
 
 extern "C" int ig_pdff_extract(const float *rho_d, int nb, int nv, int mode, float *out_d, void *stream) {
     IG_REQUIRE(rho_d && out_d && nb > 0 && nv > 0 && nb <= 65535 && mode >= 0 && mode <= 2, IG_E_ARG, "ig_pdff_extract: bad arguments");
-    pdff_extract_kernel<<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(rho_d, nb, nv, mode, out_d);
+    if (nv % 2 == 0 && aligned16(rho_d) && (reinterpret_cast<uintptr_t>(out_d) & 7u) == 0)
+        pdff_extract_kernel<pk><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(rho_d, nb, nv, mode, out_d);
+    else
+        pdff_extract_kernel<float><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(rho_d, nb, nv, mode, out_d);
     IG_CUDA(cudaGetLastError());
     return 0;
 }

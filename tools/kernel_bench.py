@@ -185,6 +185,29 @@ def main():
     add("graph[tables+ideal_loss magpha]", "C4 at nb = 3 (train-IDEAL-single), CUDA-graph replay (latency)", nb4, 384 * 384, ne, 8 * ne + 32 + 32, graph4.replay)
     add("ig_ideal_loss[magpha]", "C4 at nb = 3 through the Python wrappers (latency)", nb4, 384 * 384, ne, 8 * ne + 32 + 32,
         lambda: ops.ideal_loss(L.MODEL_MAGPHA, mp4, a4, ops.gen_tables(te4, 1.5)))
+    # C5 consumer: forward model + the three clipped images of gen_LDM_dataset.py:216-237 in one pass (3-channel decoder maps)
+    del mp4, a4
+    torch.cuda.empty_cache()
+    nb, H, W = 64, 384, 384
+    nv = H * W
+    m3 = torch.from_numpy(synth.magpha_maps(8, H, W, np.random.default_rng(5), bipolar=False)).to(dev).repeat(nb // 8, 1, 1, 1, 1).contiguous()
+    tab5 = ops.gen_tables(torch.from_numpy(synth.te_orig(nb, ne)).to(dev), 1.5)
+    add("ig_ideal_decode[images]", "C5 consumer: clip |S_e|, PDFF, R2* (no complex output)", nb, nv, ne, 24 + 4 * ne + 8,
+        lambda: ops.ideal_decode(L.MODEL_MAGPHA, m3, tab5, ne))
+    add("ig_ideal_decode[images+signals]", "C5 consumer + the TFRecord's complex signals", nb, nv, ne, 24 + 4 * ne + 8 + 8 * ne,
+        lambda: ops.ideal_decode(L.MODEL_MAGPHA, m3, tab5, ne, want_shat=True))
+    del m3
+    # more than 8 echoes (train-IDEAL-TEaug.py:614-618 trains with 3 .. 12): forward, LS solve and the C2 objective at ne = 12
+    ne12 = 12
+    torch.cuda.empty_cache()
+    maps, te, tab, acqs = make(nb, H, W, ne12)
+    pm = (maps[:, 2:3] * 0.95).contiguous()
+    add("ig_ideal_fwd[wfpm]", "ne = 12 forward", nb, nv, ne12, 24 + 8 * ne12, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne12))
+    add("ig_get_rho_fwd", "ne = 12 LS solve", nb, nv, ne12, 8 * ne12 + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm, tab))
+    add("ig_a2a_loss", "ne = 12 C2 fused objective (ring, y parked in the stage)", nb, nv, ne12, 8 * ne12 + 8 + 8, lambda: ops.a2a_loss(acqs, pm, tab))
+    up12 = torch.randn_like(acqs)
+    add("ig_a2a_bwd", "ne = 12 acq_to_acq adjoint (dPM only; plain kernel)", nb, nv, ne12, 8 * ne12 + 8 + 8 * ne12 + 8,
+        lambda: ops.a2a_bwd(acqs, pm, tab, None, up12, need_acqs=False))
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
 

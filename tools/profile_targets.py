@@ -14,7 +14,7 @@ from idealgan import _lib as L  # noqa: E402
 from idealgan import ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
-acqs, pm, te = bench.build_device_inputs(dev, 1234)
+acqs, pm, te, _ = bench.build_device_inputs(dev, 1234)
 nb, ne, H, W, _ = acqs.shape
 tab = ops.gen_tables(te, 1.5)
 g = torch.Generator(device=dev)
