@@ -29,6 +29,7 @@ mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
 mag = torch.sqrt((acqs ** 2).sum(-1, keepdim=True)).contiguous()
 _, _, demod_s, ls_s, _ = ops.cse_mag_fwd(mag, rm.reshape(nb, 1, H, W, 1), tab)
 var5 = torch.rand((nb, 5, H, W, 2), device=dev, generator=g) * 1e-3
+mp3 = mp[..., :3].contiguous()
 targets = [
     lambda: ops.a2a_loss(acqs, pm, tab),
     lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True),
@@ -42,6 +43,13 @@ targets = [
     lambda: ops.get_rho_fwd(acqs, pm, tab),
     lambda: ops.mag_regs(ls_s, demod_s, rm.reshape(nb, 1, H, W, 1), (0.1, 0.2, 0.3, 0.4)),
     lambda: ops.roi_maps(maps, var5, "PDFF-var"),
+    lambda: ops.ideal_decode(L.MODEL_MAGPHA, mp3, tab, ne),
+    lambda: ops.ideal_decode(L.MODEL_MAGPHA, mp3, tab, ne, want_shat=True),
+    lambda: ops.pdff_extract(up_rho),
+    lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab),
+    lambda: ops.cse_mag_fwd(mag, rm.reshape(nb, 1, H, W, 1), tab),
+    lambda: ops.a2a_fwd(acqs, pm, tab),
+    lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=False),
 ]
 reps = int(os.environ.get("IG_PROFILE_REPS", "2"))
 for fn in targets:
