@@ -439,6 +439,8 @@ int a2a_bwd_ring(const float *acqs, const float *pm, long pm_bstride, const floa
                  const float *g_shat, float *g_acqs, float *g_pm, cudaStream_t st);
 int magpha_loss_ring(const float *maps, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *gmaps, float *shat,
                      float *loss, void *scratch, cudaStream_t st);
+int pdff_unc_ring(const float *acqs, const float *phi_mean, const float *phi_var, const float *r2_mean, const float *r2_var, const float *tab, int nb,
+                  int ne, int nv, float r2_sc, float *rho, float *cov, cudaStream_t st);
 int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,
                          const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
                          float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st);

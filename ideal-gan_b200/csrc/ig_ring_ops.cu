@@ -424,4 +424,134 @@ int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, co
     return go(std::integral_constant<int, 8>{});
 }
 
+// =================================================================================================
+// PDFF_uncertainty: per-voxel weighted least squares with an echo-wise noise model (math: ig_tier2.cu, pdff_unc_kernel;
+// IDEAL_model.py:628-706).  The plain kernel keeps six modulators in registers on scalar lanes (1080 instructions per voxel, issue-bound at
+// 51 % of the HBM rate); its packed instantiation needs 112 registers and lost to its own dependency chains at 16 warps per SM.  Here the
+// echoes come from the stage, so the second pass re-forms the modulator instead of holding it, and the two voxels of a lane share every
+// instruction of the fit on f32x2 lanes.
+// =================================================================================================
+struct PdffUncRingParams {
+    const float *acqs, *phi_mean, *phi_var, *r2_mean, *r2_var, *tab;
+    float *rho, *cov, *loss;
+    void *scratch;
+    int nb, ne, nv, tile_stride;
+    float r2_sc, inv_n;
+};
+
+template <int NE, bool EXACT> struct PdffUncOp {
+    using Params = PdffUncRingParams;
+    struct Shared {};
+    static constexpr int kNE = NE, kMaps = 5;
+    static constexpr bool kExact = EXACT, kDynamic = false, kLoss = false, kWritesStage = false;
+    static constexpr int fpv(int m) { return m == 0 ? 2 : 1; }
+    static constexpr int planes_max(int m) { return m == 0 ? NE : 1; }
+    static constexpr int kStageBytes = NE * kRingTileVox * 8 + 4 * kRingTileVox * 4 + ((NE * 64 + 127) / 128) * 128;
+    static constexpr int kStages = 2 * 3 * kStageBytes <= kRingSmemBudget ? 3 : 2, kMinBlocks = 2;
+    __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : ((m >= 3 && !p.r2_mean) ? 0 : 1); }
+    __device__ static void prologue(Shared &) {}
+
+    __device__ static __forceinline__ void chunk(const Params &p, Shared &, unsigned char *stage, const SampleTab<NE> &T, int slot, int b, int v0,
+                                                 bool active, int ne, float &) {
+        using Lay = RingLayout<PdffUncOp>;
+        if (!active) return;
+        const float4 *sS = reinterpret_cast<const float4 *>(stage + Lay::off(0)) + slot;
+        const bool r2 = p.r2_mean != nullptr;
+        const pk zero = splat<pk>(0.f);
+        pk phi_t, s_phi, r2s = zero, s_r = zero;
+        phi_t.d = reinterpret_cast<const float2 *>(stage + Lay::off(1))[slot];
+        s_phi.d = reinterpret_cast<const float2 *>(stage + Lay::off(2))[slot];
+        s_phi = vmul(kFmSc * kFmSc, s_phi);
+        if (r2) {
+            r2s.d = reinterpret_cast<const float2 *>(stage + Lay::off(3))[slot];
+            r2s = vmul(p.r2_sc, r2s);                                      // the stage carries the unscaled decay constant
+            s_r.d = reinterpret_cast<const float2 *>(stage + Lay::off(4))[slot];
+            s_r = vmul(p.r2_sc * p.r2_sc, s_r);
+        }
+        cx<pk> q_w = czero<pk>(), q_f = czero<pk>();                        // M^+ Wm
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (EXACT || e < ne) {
+                const EchoRec R = T.r[e];
+                const Mod<pk> m = modulator_rec<pk, false, false>(R, phi_t, r2s, zero);
+                const cx<pk> wm{vmul(m.dinv, m.c), vneg(vmul(m.dinv, m.s))};
+                cmac(q_w, R.pw_re, R.pw_im, wm);
+                cmac(q_f, R.pf_re, R.pf_im, wm);
+            }
+        }
+        // normal equations of the weighted fit: G = M^H W M (Hermitian 2x2), rhs = M^H W y
+        pk g00 = zero, g11 = zero;
+        cx<pk> g01 = czero<pk>(), r0 = czero<pk>(), r1 = czero<pk>();
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (EXACT || e < ne) {
+                const EchoRec R = T.r[e];
+                const Mod<pk> m = modulator_rec<pk, false, false>(R, phi_t, r2s, zero);
+                const float k = kTwoPi * R.te;
+                pk Vv = vsub(splat<pk>(1.0f), fast_ex2(vmul(-k * k * kLog2e, s_phi)));
+                if (r2) Vv = vfma(vmul(R.te * R.te, m.dinv), s_r, Vv);               // e^{te mu} is the demodulator's own growth factor
+                const cx<pk> wm{vmul(m.dinv, m.c), vneg(vmul(m.dinv, m.s))};
+                const cx<pk> pw = caffine(q_w, R.c_re, R.c_im, q_f);                  // (M M^+ Wm)_e
+                const cx<pk> res{vsub(wm.re, pw.re), vsub(wm.im, pw.im)};              // (P0 Wm)_e
+                const pk g2 = vmul(vmul(m.d, m.d), vfma(res.re, res.re, vmul(res.im, res.im)));
+                const float4 q = sS[e * kPlaneF4];
+                const cx<pk> S{mk(q.x, q.z), mk(q.y, q.w)};
+                const pk s2 = vfma(S.re, S.re, vmul(S.im, S.im));
+                const pk den = vmul(Vv, vadd(g2, s2));
+                const pk w = mk(den.d.x != 0.f ? rcp_ftz(den.d.x) : 0.f, den.d.y != 0.f ? rcp_ftz(den.d.y) : 0.f);
+                const cx<pk> y = demod(m, S);
+                const float cr = R.c_re, ci = R.c_im;
+                g00 = vadd(g00, w);
+                g01.re = vfma(cr, w, g01.re);
+                g01.im = vfma(ci, w, g01.im);
+                g11 = vfma(cr * cr + ci * ci, w, g11);
+                r0.re = vfma(w, y.re, r0.re);
+                r0.im = vfma(w, y.im, r0.im);
+                r1.re = vfma(w, vfma(ci, y.im, vmul(cr, y.re)), r1.re);                 // conj(c) y
+                r1.im = vfma(w, vfma(-ci, y.re, vmul(cr, y.im)), r1.im);
+            }
+        }
+        // C = G^-1 = 1/det [[g11, -g01], [-conj(g01), g00]]
+        const pk det = vsub(vmul(g00, g11), vfma(g01.re, g01.re, vmul(g01.im, g01.im)));
+        const pk id = mk(1.0f / det.d.x, 1.0f / det.d.y);
+        const pk c00 = vmul(g11, id), c11 = vmul(g00, id);
+        const cx<pk> c01{vneg(vmul(g01.re, id)), vneg(vmul(g01.im, id))};
+        const cx<pk> rho_w{vfma(c00, r0.re, vsub(vmul(c01.re, r1.re), vmul(c01.im, r1.im))), vfma(c00, r0.im, vfma(c01.re, r1.im, vmul(c01.im, r1.re)))};
+        const cx<pk> rho_f{vfma(c11, r1.re, vfma(c01.re, r0.re, vmul(c01.im, r0.im))), vfma(c11, r1.im, vsub(vmul(c01.re, r0.im), vmul(c01.im, r0.re)))};
+        const float inv = 1.0f / kRhoSc, inv2 = 1.0f / (kRhoSc * kRhoSc);
+        const int nv = p.nv;
+        float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+        st_cx(rho_b, v0, cx<pk>{vmul(inv, rho_w.re), vmul(inv, rho_w.im)});
+        st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<pk>{vmul(inv, rho_f.re), vmul(inv, rho_f.im)});
+        const pk m01 = vfma(c01.re, c01.re, vmul(c01.im, c01.im));
+        const pk a01 = vmul(inv2, mk(sqrtf(m01.d.x), sqrtf(m01.d.y)));
+        float *cov_b = p.cov + static_cast<size_t>(b) * 4 * nv;
+        st_real(cov_b, v0, vmul(inv2, mk(fabsf(c00.d.x), fabsf(c00.d.y))));
+        st_real(cov_b + nv, v0, a01);
+        st_real(cov_b + 2 * static_cast<size_t>(nv), v0, a01);
+        st_real(cov_b + 3 * static_cast<size_t>(nv), v0, vmul(inv2, mk(fabsf(c11.d.x), fabsf(c11.d.y))));
+    }
+};
+
+int pdff_unc_ring(const float *acqs, const float *phi_mean, const float *phi_var, const float *r2_mean, const float *r2_var, const float *tab, int nb,
+                  int ne, int nv, float r2_sc, float *rho, float *cov, cudaStream_t st) {
+    auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+    if (ne > 8 || nv % 128 != 0 || !aligned16(rho) || !al8(cov) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24)) return IG_E_UNSUPPORTED;
+    PdffUncRingParams p{};
+    p.acqs = acqs; p.phi_mean = phi_mean; p.phi_var = phi_var; p.r2_mean = r2_mean; p.r2_var = r2_var; p.tab = tab; p.rho = rho; p.cov = cov;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    RingMaps m{};
+    if (!ring_tensor_map(&m.m[0], acqs, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
+    if (!ring_tensor_map(&m.m[1], phi_mean, nv, 1, nb, nv, 1) || !ring_tensor_map(&m.m[2], phi_var, nv, 1, nb, nv, 1)) return IG_E_UNSUPPORTED;
+    if (r2_mean && (!ring_tensor_map(&m.m[3], r2_mean, nv, 1, nb, nv, 1) || !ring_tensor_map(&m.m[4], r2_var, nv, 1, nb, nv, 1))) return IG_E_UNSUPPORTED;
+    auto go = [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (ne == NE) return ring_launch<PdffUncOp<NE, true>>(p, m, st);
+        return ring_launch<PdffUncOp<NE, false>>(p, m, st);
+    };
+    if (ne <= 4) return go(std::integral_constant<int, 4>{});
+    if (ne <= 6) return go(std::integral_constant<int, 6>{});
+    return go(std::integral_constant<int, 8>{});
+}
+
 }  // namespace ig

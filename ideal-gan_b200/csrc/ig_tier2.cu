@@ -110,6 +110,75 @@ template <int NE> __device__ __forceinline__ void stage_mag_table(MagTab<NE> &t,
     __syncthreads();
 }
 
+// Forward pass with two neighbouring voxels per thread (8-byte streaming loads / stores, f32x2 arithmetic for the fit): the
+// one-voxel kernel below moved 100 bytes per voxel in 4-byte transactions and was bound by instruction issue (78 % of the slots,
+// a third of them load / store instructions) at 67 % of the HBM rate.  Same arithmetic; the eigen-decomposition runs per lane.
+__device__ __forceinline__ pk sqrt_approx(pk x) {
+    pk r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.d.x) : "f"(x.d.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r.d.y) : "f"(x.d.y));
+    return r;
+}
+template <int NE> __global__ void __launch_bounds__(kThreads) cse_mag_fwd2_kernel(const CseParams p) {
+    __shared__ MagTab<NE> T;
+    const int b = blockIdx.y;
+    stage_mag_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne);
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (v >= p.nv) return;
+    const int nv = p.nv, ne = p.ne;
+    const size_t eb = static_cast<size_t>(b) * ne * nv, vb = static_cast<size_t>(b) * nv;
+    const pk R = vmul(p.r2_sc * kLog2e, ld_real(p.r2 + vb, v, pk{}));          // R2* in units of log2(e): the growth factor is one EX2
+    pk S[NE], y[NE], wm[NE];
+    pk a = splat<pk>(0.f), bb = a, c = a;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (e < ne) S[e] = ld_real(p.mag + eb + static_cast<size_t>(e) * nv, v, pk{});
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            wm[e] = fast_ex2(vmul(T.te[e], R));
+            const pk t = vmul(wm[e], S[e]);
+            y[e] = vmul(t, t);
+            a = vfma(T.p0[e], y[e], a);
+            bb = vfma(T.p1[e], y[e], bb);
+            c = vfma(T.p2[e], y[e], c);
+        }
+    }
+    const float inv_rho = 1.0f / kRhoSc, inv_rho2 = 1.0f / (kRhoSc * kRhoSc);
+    const Eig e0 = eig_fwd(a.d.x, bb.d.x, c.d.x), e1 = eig_fwd(a.d.y, bb.d.y, c.d.y);
+    if (p.rho) {
+        st_real(p.rho + (static_cast<size_t>(b) * 2 + 0) * nv, v, mk(e0.x * inv_rho, e1.x * inv_rho));
+        st_real(p.rho + (static_cast<size_t>(b) * 2 + 1) * nv, v, mk(e0.y * inv_rho, e1.y * inv_rho));
+    }
+    if (p.ls) {
+        st_real(p.ls + (static_cast<size_t>(b) * 3 + 0) * nv, v, vmul(inv_rho2, a));
+        st_real(p.ls + (static_cast<size_t>(b) * 3 + 1) * nv, v, vmul(inv_rho2, bb));
+        st_real(p.ls + (static_cast<size_t>(b) * 3 + 2) * nv, v, vmul(inv_rho2, c));
+    }
+    if (p.unc) st_real(p.unc + vb, v, mk(e0.ratio, e1.ratio));
+    pk Rnu = splat<pk>(0.f);
+    if (p.r2nu) Rnu = vmul(p.r2_sc * kLog2e, ld_real(p.r2nu + vb, v, pk{}));
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e < ne) {
+            const size_t o = eb + static_cast<size_t>(e) * nv;
+            if (p.fit) {
+                const pk f = vfma(T.a2[e], c, vfma(T.a1[e], bb, a));
+                const pk sh = vmul(sqrt_approx(f), fast_ex2(vneg(vmul(T.te[e], R))));                 // sqrt(fit) e^{-te R}
+                st_real(p.fit + o, v, mk(f.d.x > 1e-6f ? sh.d.x : 0.f, f.d.y > 1e-6f ? sh.d.y : 0.f));
+            }
+            if (p.demod) {
+                if (p.r2nu) {
+                    const pk t = vmul(fast_ex2(vmul(T.te[e], Rnu)), S[e]);
+                    st_real(p.demod + o, v, vmul(t, t));
+                } else {
+                    st_real(p.demod + o, v, y[e]);
+                }
+            }
+        }
+    }
+}
+
 template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) cse_mag_kernel(const CseParams p) {
     __shared__ MagTab<NE> T;
     const int b = blockIdx.y;
@@ -434,7 +503,11 @@ extern "C" int ig_cse_mag_fwd(const float *mag_d, const float *r2_d, const float
     p.rho = rho_d; p.fit = fit_d; p.demod = demod_d; p.ls = ls_d; p.unc = unc_d;
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        cse_mag_kernel<NE, false><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+        if (nv % 2 == 0 && al8(mag_d) && al8(r2_d) && al8(r2nu_d) && al8(rho_d) && al8(fit_d) && al8(demod_d) && al8(ls_d) && al8(unc_d))
+            cse_mag_fwd2_kernel<NE><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else
+            cse_mag_kernel<NE, false><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         IG_CUDA(cudaGetLastError());
         return 0;
     });
@@ -496,6 +569,11 @@ extern "C" int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const f
     PdffUncParams p{};
     p.acqs = acqs_d; p.phi_mean = phi_mean_d; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d;
     p.rho = rho_d; p.cov = cov_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
+    {
+        // 128-voxel rows, <= 8 echoes: the packed fit on the generic TMA ring (ig_ring_ops.cu, PdffUncOp)
+        const int rc = pdff_unc_ring(acqs_d, phi_mean_d, phi_var_d, r2_mean_d, r2_var_d, tab_d, nb, ne, nv, r2_sc, rho_d, cov_d, static_cast<cudaStream_t>(stream));
+        if (rc != IG_E_UNSUPPORTED) return rc;
+    }
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
         // measured at 64 x 384 x 384 x 6: one voxel per thread 0.272 ms (58 registers, issue slots 79 % busy); the packed instantiation

@@ -89,3 +89,38 @@ def test_uq_ring_equals_plain_kernel_on_unaligned_copy(shape):
     assert abs(a[0].item() - b[0].item()) <= 2e-6 * abs(b[0].item())
     for x, y, what in zip(a[1:], b[1:], ("g_pm", "g_phi_var", "g_r2_mean", "g_r2_var", "rho")):
         assert_close(x.cpu().numpy(), y.cpu().numpy(), 5e-6, what)
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 16, 6), (2, 32, 48, 5), (1, 384, 384, 6), (2, 64, 96, 8), (2, 64, 64, 3)])
+@pytest.mark.parametrize("rem", [False, True], ids=["with-R2-moments", "rem_R2"])
+def test_pdff_uncertainty_ring_vs_plain_kernel_and_fp64_oracle(shape, rem):
+    """PDFF_uncertainty on the generic ring (128-voxel rows, <= 8 echoes) against the plain one-voxel-per-thread kernel (forced by a
+    moment map that is 8- but not 16-byte aligned) and against the fp64 oracle, at the operator's documented 3e-5."""
+    from oracle import ideal_oracle as orc
+    nb, H, W, ne = shape
+    rng = np.random.default_rng(91 + nb + ne)
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0, masked=False)
+    te = synth.te_random(nb, ne, rng)
+    sig = orc.IDEAL_model(torch.from_numpy(maps), [1.5, torch.from_numpy(te)]).numpy()
+    acqs = synth.add_noise(sig, rng)
+    phi_m = np.ascontiguousarray(maps[:, 2:3, :, :, 0:1])
+    r2_m = np.ascontiguousarray(maps[:, 2:3, :, :, 1:2])
+    phi_v = rng.uniform(1e-5, 2e-3, size=phi_m.shape).astype(np.float32)
+    r2_v = rng.uniform(1e-5, 2e-3, size=phi_m.shape).astype(np.float32)
+    d = lambda x: torch.from_numpy(x).cuda()      # noqa: E731
+    tab = ops.gen_tables(d(te), 1.5)
+    args = (d(acqs), d(phi_m), d(phi_v), None if rem else d(r2_m), None if rem else d(r2_v), tab)
+    rho, cov = ops.pdff_unc(*args)
+    buf = torch.empty(phi_v.size + 2, device="cuda")
+    pv_off = buf[2:].view(phi_v.shape)
+    pv_off.copy_(d(phi_v))
+    assert pv_off.data_ptr() % 16 == 8
+    rho_p, cov_p = ops.pdff_unc(args[0], args[1], pv_off, args[3], args[4], tab)
+    assert_close(rho.cpu().numpy(), rho_p.cpu().numpy(), 1e-5, "rho ring vs plain")
+    assert_close(cov.cpu().numpy(), cov_p.cpu().numpy(), 1e-5, "cov ring vs plain")
+    if H * W <= 4096:
+        T = torch.from_numpy
+        rho64, cov64 = orc.PDFF_uncertainty(T(acqs), orc.Moments(T(phi_m), T(phi_v)), orc.Moments(T(r2_m), T(r2_v)), te=T(te), rem_R2=rem,
+                                            rdtype=torch.float64)
+        assert_close(rho.cpu().numpy(), rho64.numpy(), 3e-5, "rho vs fp64 oracle")
+        assert_close(cov.cpu().numpy(), cov64.numpy(), 3e-5, "cov vs fp64 oracle")

@@ -207,6 +207,37 @@ def test_cse_mag_with_autograd(golden, name):
     assert_close(host(gr2), host(gr64), 3e-5, "grad r2 vs fp64")
 
 
+@pytest.mark.parametrize("hw", [(7, 9), (24, 16), (384, 384)], ids=["odd-7x9-scalar-lanes", "even-24x16-packed", "384x384-packed"])
+@pytest.mark.parametrize("r2_prob", [False, True])
+def test_cse_mag_forward_both_lane_paths_vs_oracle(hw, r2_prob):
+    """ig_cse_mag_fwd has a two-voxel-per-thread kernel (even nv, 8-byte aligned planes) and the one-voxel kernel for everything else:
+    both against the fp64 oracle, with and without the R2_prob branch (`.nu`, IDEAL_model.py:335-338), incl. the BASELINE slice size."""
+    H, W = hw
+    nb, ne = 2, 6
+    rng = np.random.default_rng(H * W)
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0, masked=False)
+    maps[:, 0:2, :, :, 1] = 0.0
+    maps[:, 0:2, :, :, 0] = np.abs(maps[:, 0:2, :, :, 0]) + 0.1
+    te = synth.te_random(nb, ne, rng)
+    sig = orc.IDEAL_model(torch.from_numpy(maps), [1.5, torch.from_numpy(te)]).numpy()
+    mag = np.sqrt((sig ** 2).sum(-1, keepdims=True)).astype(np.float32)
+    r2 = np.ascontiguousarray(maps[:, 2:3, :, :, 1:2])
+    nu = (r2 * np.float32(1.07)).astype(np.float32)
+
+    class Prob:                       # what the reference reads of a tfp distribution when R2_prob (:335-338)
+        def __init__(self, t, n):
+            self.tensor, self.nu = t, n
+
+    arg_dev = Prob(dev(r2), dev(nu)) if r2_prob else dev(r2)
+    arg_ref = Prob(torch.from_numpy(r2), torch.from_numpy(nu)) if r2_prob else torch.from_numpy(r2)
+    got = wf.CSE_mag(dev(mag), arg_dev, [1.5, dev(te)], demod_signal=True, R2_prob=r2_prob)
+    got_unc = wf.CSE_mag(dev(mag), arg_dev, [1.5, dev(te)], uncertainty=True, R2_prob=r2_prob)[2]
+    ref = orc.CSE_mag(torch.from_numpy(mag), arg_ref, [1.5, torch.from_numpy(te)], demod_signal=True, R2_prob=r2_prob, rdtype=torch.float64)
+    for k, g_, r_ in zip(("rho", "fit", "demod", "ls"), got, ref):
+        assert_close(host(g_), r_.numpy(), 3e-5, k)
+    assert float(got_unc.abs().max()) <= 1e-4          # noiseless magnitudes are rank one: lambda_min / lambda_max is rounding noise
+
+
 @pytest.mark.parametrize("name", ["unc_1p5", "unc_3p0_rem"])
 def test_acq_uncertainty_with_autograd(golden, name):
     g = golden("tier2")

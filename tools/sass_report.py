@@ -3,7 +3,8 @@
 of (TMA tensor / bulk copies, mbarrier operations, packed f32x2 arithmetic, SFU calls), and registers / spills / shared memory
 from the ptxas logs of the same build.
 
-    python tools/sass_report.py > profiles/sass_rNN.md          (after `make -C ideal-gan_b200/csrc`)
+    python tools/sass_report.py [regex ...] > profiles/sass_rNN.md          (after `make -C ideal-gan_b200/csrc`; the regexes select the
+                                                                             kernels of the main table, default all)
 """
 import collections
 import os
@@ -88,12 +89,15 @@ def main():
     print("No `UTC*MMA` / TMEM instruction is present and none is expected: the largest contraction on this path is 2 x ne per voxel, in fp32.\n")
     focus = [a for a in sys.argv[1:] if not a.startswith("-")]
     cols = ["regs", "spill st/ld B", "smem B"] + list(PATTERNS)
+    if focus:
+        print("Main table: kernels matching " + ", ".join(f"`{f}`" for f in focus) + " (the instantiations the BASELINE configurations launch at ne = 6, "
+              "the ne = 12 ones, and the kernels without an echo-count template).\n")
     print("| kernel | " + " | ".join(cols) + " |")
     print("|---|" + "---|" * len(cols))
     rows = []
     for mangled, c in kernels.items():
         name = short(dm.get(mangled, mangled))
-        if focus and not any(f in name for f in focus):
+        if focus and not any(re.search(f, name) for f in focus):
             continue
         i = info.get(mangled, {})
         rows.append((name, i, c))
