@@ -428,8 +428,8 @@ int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, co
 // PDFF_uncertainty: per-voxel weighted least squares with an echo-wise noise model (math: ig_tier2.cu, pdff_unc_kernel;
 // IDEAL_model.py:628-706).  The plain kernel keeps six modulators in registers on scalar lanes (1080 instructions per voxel, issue-bound at
 // 51 % of the HBM rate); its packed instantiation needs 112 registers and lost to its own dependency chains at 16 warps per SM.  Here the
-// echoes come from the stage, so the second pass re-forms the modulator instead of holding it, and the two voxels of a lane share every
-// instruction of the fit on f32x2 lanes.
+// echoes come from the stage and the demodulated echoes go back into it, the demodulator of each echo is the only per-echo state held
+// in registers, and the two voxels of a lane share every instruction of the fit on f32x2 lanes.
 // =================================================================================================
 struct PdffUncRingParams {
     const float *acqs, *phi_mean, *phi_var, *r2_mean, *r2_var, *tab;
@@ -443,7 +443,7 @@ template <int NE, bool EXACT> struct PdffUncOp {
     using Params = PdffUncRingParams;
     struct Shared {};
     static constexpr int kNE = NE, kMaps = 5;
-    static constexpr bool kExact = EXACT, kDynamic = false, kLoss = false, kWritesStage = false;
+    static constexpr bool kExact = EXACT, kDynamic = false, kLoss = false, kWritesStage = true;       // y_e is parked in the echo planes
     static constexpr int fpv(int m) { return m == 0 ? 2 : 1; }
     static constexpr int planes_max(int m) { return m == 0 ? NE : 1; }
     static constexpr int kStageBytes = NE * kRingTileVox * 8 + 4 * kRingTileVox * 4 + ((NE * 64 + 127) / 128) * 128;
@@ -455,7 +455,6 @@ template <int NE, bool EXACT> struct PdffUncOp {
                                                  bool active, int ne, float &) {
         using Lay = RingLayout<PdffUncOp>;
         if (!active) return;
-        const float4 *sS = reinterpret_cast<const float4 *>(stage + Lay::off(0)) + slot;
         const bool r2 = p.r2_mean != nullptr;
         const pk zero = splat<pk>(0.f);
         pk phi_t, s_phi, r2s = zero, s_r = zero;
@@ -468,38 +467,48 @@ template <int NE, bool EXACT> struct PdffUncOp {
             s_r.d = reinterpret_cast<const float2 *>(stage + Lay::off(4))[slot];
             s_r = vmul(p.r2_sc * p.r2_sc, s_r);
         }
+        // Pass 1: the demodulator Wm_e = e^{te R} conj(u_e) is formed ONCE per echo and kept (two register pairs); the demodulated echo
+        // y_e = Wm_e S_e replaces the raw echo in the thread's own 16 bytes of the stage.  Everything pass 2 needs follows from those two:
+        // |S_e|^2 = d_e^2 |y_e|^2 and d_e = |Wm_e|^-1, so no modulator is formed twice and no echo is read twice.
         cx<pk> q_w = czero<pk>(), q_f = czero<pk>();                        // M^+ Wm
+        cx<pk> wm[NE];
+        float4 *sY = reinterpret_cast<float4 *>(stage + Lay::off(0)) + slot;
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (EXACT || e < ne) {
                 const EchoRec R = T.r[e];
-                const Mod<pk> m = modulator_rec<pk, false, false>(R, phi_t, r2s, zero);
-                const cx<pk> wm{vmul(m.dinv, m.c), vneg(vmul(m.dinv, m.s))};
-                cmac(q_w, R.pw_re, R.pw_im, wm);
-                cmac(q_f, R.pf_re, R.pf_im, wm);
+                pk c, sn;
+                unit_phasor(vmul(R.kphi, phi_t), c, sn);
+                const pk dinv = fast_ex2(vneg(vmul(R.kdec, r2s)));
+                wm[e] = cx<pk>{vmul(dinv, c), vneg(vmul(dinv, sn))};
+                const cx<pk> y = conj_rot(wm[e].re, vneg(wm[e].im), sY[e * kPlaneF4]);      // (re - i(-im)) ... = Wm S
+                sY[e * kPlaneF4] = make_float4(y.re.d.x, y.re.d.y, y.im.d.x, y.im.d.y);
+                cmac(q_w, R.pw_re, R.pw_im, wm[e]);
+                cmac(q_f, R.pf_re, R.pf_im, wm[e]);
             }
         }
-        // normal equations of the weighted fit: G = M^H W M (Hermitian 2x2), rhs = M^H W y
+        // Pass 2: normal equations of the weighted fit, G = M^H W M (Hermitian 2x2), rhs = M^H W y, with
+        // 1 / w_e = V_e (d_e^2 |(P0 Wm)_e|^2 + |S_e|^2) = (vphi_e d_e^2 + te_e^2 s_r d_e) (|(P0 Wm)_e|^2 + |y_e|^2)       (V_e = vphi_e + te_e^2 s_r / d_e)
         pk g00 = zero, g11 = zero;
         cx<pk> g01 = czero<pk>(), r0 = czero<pk>(), r1 = czero<pk>();
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (EXACT || e < ne) {
                 const EchoRec R = T.r[e];
-                const Mod<pk> m = modulator_rec<pk, false, false>(R, phi_t, r2s, zero);
                 const float k = kTwoPi * R.te;
-                pk Vv = vsub(splat<pk>(1.0f), fast_ex2(vmul(-k * k * kLog2e, s_phi)));
-                if (r2) Vv = vfma(vmul(R.te * R.te, m.dinv), s_r, Vv);               // e^{te mu} is the demodulator's own growth factor
-                const cx<pk> wm{vmul(m.dinv, m.c), vneg(vmul(m.dinv, m.s))};
+                const pk n2 = vfma(wm[e].re, wm[e].re, vmul(wm[e].im, wm[e].im));     // |Wm|^2 = 1 / d^2
+                const pk d = mk(rsqrt_ftz(n2.d.x), rsqrt_ftz(n2.d.y));
+                const pk d2 = vmul(d, d);
+                const pk vphi = one_minus_exp_neg_fast(vmul(k * k, s_phi));
+                pk vd = vmul(vphi, d2);
+                if (r2) vd = vfma(vmul(R.te * R.te, s_r), d, vd);
                 const cx<pk> pw = caffine(q_w, R.c_re, R.c_im, q_f);                  // (M M^+ Wm)_e
-                const cx<pk> res{vsub(wm.re, pw.re), vsub(wm.im, pw.im)};              // (P0 Wm)_e
-                const pk g2 = vmul(vmul(m.d, m.d), vfma(res.re, res.re, vmul(res.im, res.im)));
-                const float4 q = sS[e * kPlaneF4];
-                const cx<pk> S{mk(q.x, q.z), mk(q.y, q.w)};
-                const pk s2 = vfma(S.re, S.re, vmul(S.im, S.im));
-                const pk den = vmul(Vv, vadd(g2, s2));
+                const cx<pk> res{vsub(wm[e].re, pw.re), vsub(wm[e].im, pw.im)};        // (P0 Wm)_e
+                const float4 q = sY[e * kPlaneF4];
+                const cx<pk> y{mk(q.x, q.y), mk(q.z, q.w)};
+                const pk sum = vadd(vfma(res.re, res.re, vmul(res.im, res.im)), vfma(y.re, y.re, vmul(y.im, y.im)));
+                const pk den = vmul(vd, sum);
                 const pk w = mk(den.d.x != 0.f ? rcp_ftz(den.d.x) : 0.f, den.d.y != 0.f ? rcp_ftz(den.d.y) : 0.f);
-                const cx<pk> y = demod(m, S);
                 const float cr = R.c_re, ci = R.c_im;
                 g00 = vadd(g00, w);
                 g01.re = vfma(cr, w, g01.re);

@@ -404,7 +404,7 @@ template <int NE, typename V> __global__ void __launch_bounds__(kThreads) pdff_u
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
             const float te = T.r[e].te, k = kTwoPi * te;
-            V Vv = vsub(splat<V>(1.0f), fast_ex2(vmul(-k * k * kLog2e, s_phi)));
+            V Vv = one_minus_exp_neg_fast(vmul(k * k, s_phi));
             if (r2) Vv = vfma(vmul(te * te, m[e].dinv), s_r, Vv);                      // e^{te mu} is the demodulator's own growth factor
             const cx<V> wm{vmul(m[e].dinv, m[e].c), vneg(vmul(m[e].dinv, m[e].s))};
             const cx<V> pw = caffine(q_w, T.r[e].c_re, T.r[e].c_im, q_f);              // (M M^+ Wm)_e

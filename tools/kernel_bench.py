@@ -104,8 +104,16 @@ def main():
     r2map = pm[..., 1:2].contiguous().reshape(nb, 1, H, W, 1)
     add("ig_cse_mag_fwd", "CSE_mag (rho, fit, demod, ls, unc)", nb, nv, ne, 12 * ne + 28,
         lambda: ops.cse_mag_fwd(mag, r2map, tab))
+    ups_cse = [torch.randn((nb, c_, H, W, 1), device=dev, generator=g) for c_ in (2, ne, ne, 3, 1)]
+    add("ig_cse_mag_bwd", "CSE_mag adjoint (all five upstreams -> d mag, d R2*)", nb, nv, ne, 4 * ne + 4 + 4 * (2 + ne + ne + 3 + 1) + 4 * ne + 4,
+        lambda: ops.cse_mag_bwd(mag, r2map, tab, ups_cse))
+    del ups_cse
     rho_hat, _ = ops.a2a_fwd(acqs, pm, tab)
     add("ig_acq_unc_fwd", "acq_uncertainty", nb, nv, ne, 16 + 12 + 8 * ne, lambda: ops.acq_unc_fwd(rho_hat, pv, rm, rv, tab, ne))
+    up_var = torch.randn((nb, ne, H, W, 2), device=dev, generator=g)
+    add("ig_acq_unc_bwd", "acq_uncertainty adjoint (d phi_var, d R2* mean, d R2* var)", nb, nv, ne, 16 + 12 + 8 * ne + 12,
+        lambda: ops.acq_unc_bwd(rho_hat, pv, rm, rv, tab, ne, up_var))
+    del up_var
     add("ig_pdff_unc", "PDFF_uncertainty (weighted LS per voxel)", nb, nv, ne, 8 * ne + 16 + 16 + 16,
         lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab))
     add("ig_pdff_extract", "PDFF map", nb, nv, ne, 16 + 4, lambda: ops.pdff_extract(rho_hat))
