@@ -119,14 +119,14 @@ def test_pdff_uncertainty_ring_vs_plain_kernel_and_fp64_oracle(shape, rem):
     rho_p, cov_p = ops.pdff_unc(args[0], args[1], pv_off, args[3], args[4], tab)
     # The fit is ill-conditioned on a few voxels of a slice (weights 1 / Sigma, Sigma ~ 1e-4): the reference's own algorithm evaluated in
     # fp32 (the oracle's complex64 restatement) is 2-3e-5 away from its fp64 evaluation on the worst voxel of a 384 x 384 slice.  The bar for
-    # a kernel is therefore the larger of the operator's documented 3e-5 and 1.5 x that fp32-vs-fp64 distance, measured on the same data.
+    # a kernel is therefore the larger of the operator's documented 3e-5 and twice that fp32-vs-fp64 distance, measured on the same data.
     from conftest import rel_err
     T = torch.from_numpy
     mom = (orc.Moments(T(phi_m), T(phi_v)), orc.Moments(T(r2_m), T(r2_v)))
     rho64, cov64 = orc.PDFF_uncertainty(T(acqs), *mom, te=T(te), rem_R2=rem, rdtype=torch.float64)
     rho32, cov32 = orc.PDFF_uncertainty(T(acqs), *mom, te=T(te), rem_R2=rem, rdtype=torch.float32)
-    tol_rho = max(3e-5, 1.5 * rel_err(rho32.numpy(), rho64.numpy()))
-    tol_cov = max(3e-5, 1.5 * rel_err(cov32.numpy(), cov64.numpy()))
+    tol_rho = max(3e-5, 2.0 * rel_err(rho32.numpy(), rho64.numpy()))
+    tol_cov = max(3e-5, 2.0 * rel_err(cov32.numpy(), cov64.numpy()))
     assert tol_rho < 1e-4 and tol_cov < 1e-4
     for name, got_rho, got_cov in (("ring", rho, cov), ("plain", rho_p, cov_p)):
         assert_close(got_rho.cpu().numpy(), rho64.numpy(), tol_rho, f"rho ({name} kernel) vs fp64 oracle")
