@@ -419,46 +419,65 @@ struct UncParams {
     float r2_sc;
 };
 
-template <int NE, bool BWD> __global__ void __launch_bounds__(kThreads) acq_unc_kernel(const UncParams p) {
+// V = pk: two neighbouring voxels per thread (16-byte loads of rho, 8-byte loads of the moment maps, 16- or 8-byte stores per echo);
+// V = float: odd voxel counts / unaligned planes.  (One voxel per thread with 4- and 8-byte accesses measured 88 % / 74 % of the HBM rate.)
+template <int NE, bool BWD, typename V> __global__ void __launch_bounds__(kThreads) acq_unc_kernel(const UncParams p) {
     __shared__ SampleTab<NE> T;
     const int b = blockIdx.y;
     stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, 1.0f);
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
     if (v >= p.nv) return;
     const int nv = p.nv, ne = p.ne, ch = p.ch;
-    const size_t vb = static_cast<size_t>(b) * nv + v;
-    const float2 w2 = reinterpret_cast<const float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 0) * nv + v];
-    const float2 f2 = reinterpret_cast<const float2 *>(p.rho)[(static_cast<size_t>(b) * 2 + 1) * nv + v];
-    const cx<float> rw{kRhoSc * w2.x, kRhoSc * w2.y}, rf{kRhoSc * f2.x, kRhoSc * f2.y};
-    const float s_phi = p.phi_var[vb] * (kFmSc * kFmSc);
+    const size_t vb = static_cast<size_t>(b) * nv;
+    const V zero = splat<V>(0.f);
+    const float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
+    const cx<V> w2 = ld_cx(rho_b, v, V{}), f2 = ld_cx(rho_b + static_cast<size_t>(nv) * 2, v, V{});
+    const cx<V> rw{vmul(kRhoSc, w2.re), vmul(kRhoSc, w2.im)}, rf{vmul(kRhoSc, f2.re), vmul(kRhoSc, f2.im)};
+    const V s_phi = vmul(kFmSc * kFmSc, ld_real(p.phi_var + vb, v, V{}));
     const bool r2 = p.r2_mean != nullptr;
-    const float mu = r2 ? p.r2_mean[vb] * p.r2_sc : 0.f, s_r = r2 ? p.r2_var[vb] * (p.r2_sc * p.r2_sc) : 0.f;
-    float g_sphi = 0.f, g_mu = 0.f, g_sr = 0.f;
+    const V mu = r2 ? vmul(p.r2_sc, ld_real(p.r2_mean + vb, v, V{})) : zero;
+    const V s_r = r2 ? vmul(p.r2_sc * p.r2_sc, ld_real(p.r2_var + vb, v, V{})) : zero;
+    V g_sphi = zero, g_mu = zero, g_sr = zero;
+    [[maybe_unused]] V G[NE];
+    if constexpr (BWD) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < ne) {
+                const float *g_e = p.g_out + (static_cast<size_t>(b) * ne + e) * nv * ch;
+                if (ch == 2) {
+                    const cx<V> g2 = ld_cx(g_e, v, V{});
+                    G[e] = vadd(g2.re, g2.im);
+                } else {
+                    G[e] = ld_real(g_e, v, V{});
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
             const float te = T.r[e].te, k = kTwoPi * te, k2 = k * k;
-            const float ephi = __expf(-k2 * s_phi);
-            const float er = r2 ? __expf(-te * mu) * te * te : 0.f;
-            const cx<float> m = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
-            const float a2 = m.re * m.re + m.im * m.im;
-            const size_t o = ((static_cast<size_t>(b) * ne + e) * nv + v) * ch;
+            const V ephi = fast_ex2(vmul(-k2 * kLog2e, s_phi));
+            const V er = r2 ? vmul(te * te, fast_ex2(vmul(-te * kLog2e, mu))) : zero;
+            const cx<V> m = caffine(rw, T.r[e].c_re, T.r[e].c_im, rf);
+            const V a2 = vfma(m.re, m.re, vmul(m.im, m.im));
             if constexpr (!BWD) {
-                const float var = (1.0f - ephi + er * s_r) * a2;
-                p.out[o] = var;
-                if (ch == 2) p.out[o + 1] = var;
+                const V var = vmul(vfma(er, s_r, vsub(splat<V>(1.0f), ephi)), a2);        // 1 - e^{-x} literally, as the reference forms it
+                float *o_e = p.out + (static_cast<size_t>(b) * ne + e) * nv * ch;
+                if (ch == 2) st_cx(o_e, v, cx<V>{var, var});
+                else st_real(o_e, v, var);
             } else {
-                const float g = (ch == 2 ? p.g_out[o] + p.g_out[o + 1] : p.g_out[o]) * a2;
-                g_sphi = fmaf(g * k2, ephi, g_sphi);
-                g_mu = fmaf(-g * te, er * s_r, g_mu);
-                g_sr = fmaf(g, er, g_sr);
+                const V g = vmul(G[e], a2);
+                g_sphi = vfma(vmul(k2, g), ephi, g_sphi);
+                g_mu = vfma(vmul(-te, g), vmul(er, s_r), g_mu);
+                g_sr = vfma(g, er, g_sr);
             }
         }
     }
     if constexpr (BWD) {
-        p.g_phi_var[vb] = g_sphi * (kFmSc * kFmSc);
-        if (p.g_r2_mean) p.g_r2_mean[vb] = g_mu * p.r2_sc;
-        if (p.g_r2_var) p.g_r2_var[vb] = g_sr * (p.r2_sc * p.r2_sc);
+        st_real(p.g_phi_var + vb, v, vmul(kFmSc * kFmSc, g_sphi));
+        if (p.g_r2_mean) st_real(p.g_r2_mean + vb, v, vmul(p.r2_sc, g_mu));
+        if (p.g_r2_var) st_real(p.g_r2_var + vb, v, vmul(p.r2_sc * p.r2_sc, g_sr));
     }
 }
 
@@ -657,7 +676,11 @@ extern "C" int ig_acq_unc_fwd(const float *rho_d, const float *phi_var_d, const 
     p.nb = nb; p.ne = ne; p.nv = nv; p.ch = only_mag ? 1 : 2; p.r2_sc = r2_sc;
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        acq_unc_kernel<NE, false><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+        if (nv % 2 == 0 && aligned16(rho_d) && al8(phi_var_d) && al8(r2_mean_d) && al8(r2_var_d) && (only_mag ? al8(out_d) : aligned16(out_d)))
+            acq_unc_kernel<NE, false, pk><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else
+            acq_unc_kernel<NE, false, float><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         IG_CUDA(cudaGetLastError());
         return 0;
     });
@@ -674,7 +697,12 @@ extern "C" int ig_acq_unc_bwd(const float *rho_d, const float *phi_var_d, const 
     p.nb = nb; p.ne = ne; p.nv = nv; p.ch = only_mag ? 1 : 2; p.r2_sc = r2_sc;
     return dispatch_ne(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        acq_unc_kernel<NE, true><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+        if (nv % 2 == 0 && aligned16(rho_d) && al8(phi_var_d) && al8(r2_mean_d) && al8(r2_var_d) && (only_mag ? al8(g_out_d) : aligned16(g_out_d)) &&
+            al8(g_phi_var_d) && al8(g_r2_mean_d) && al8(g_r2_var_d))
+            acq_unc_kernel<NE, true, pk><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else
+            acq_unc_kernel<NE, true, float><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         IG_CUDA(cudaGetLastError());
         return 0;
     });

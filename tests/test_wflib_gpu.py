@@ -278,6 +278,34 @@ def test_acq_uncertainty_with_autograd(golden, name):
             assert_close(host(gr), ref, 2e-5, k)
 
 
+@pytest.mark.parametrize("hw", [(7, 9), (24, 16)], ids=["odd-7x9-scalar-lanes", "even-24x16-packed"])
+@pytest.mark.parametrize("only_mag", [False, True])
+def test_acq_uncertainty_both_lane_paths_vs_oracle(hw, only_mag):
+    """acq_uncertainty forward and adjoint on the two-voxel-per-thread kernel and on the one-voxel kernel (odd voxel count) against
+    the oracle (fp32 restatement for the values: both form 1 - exp(-x) literally; fp64 autograd for the gradients)."""
+    H, W = hw
+    nb, ne = 2, 6
+    rng = np.random.default_rng(H + W)
+    maps = synth.wfpm_maps(nb, H, W, rng, neg_r2_frac=0.0)
+    te = synth.te_random(nb, ne, rng)
+    rho = np.ascontiguousarray(maps[:, :2])
+    r2_m = np.ascontiguousarray(maps[:, 2:3, :, :, 1:2])
+    phi_v = rng.uniform(1e-5, 2e-3, size=r2_m.shape).astype(np.float32)
+    r2_v = rng.uniform(1e-5, 2e-3, size=r2_m.shape).astype(np.float32)
+    T = torch.from_numpy
+    ref = orc.acq_uncertainty(T(rho), orc.Moments(None, T(phi_v)), orc.Moments(T(r2_m), T(r2_v)), ne=ne, te=T(te), only_mag=only_mag)
+    pv, rm, rv = dev(phi_v, True), dev(r2_m, True), dev(r2_v, True)
+    var = wf.acq_uncertainty(dev(rho), Moments(None, pv), Moments(rm, rv), ne=ne, te=dev(te), only_mag=only_mag)
+    assert_close(host(var), ref.numpy(), 2e-5, "variance")
+    up = rng.standard_normal(tuple(ref.shape)).astype(np.float32)
+    p64, m64, v64 = (T(x).double().requires_grad_(True) for x in (phi_v, r2_m, r2_v))
+    ref64 = orc.acq_uncertainty(T(rho).double(), orc.Moments(None, p64), orc.Moments(m64, v64), ne=ne, te=T(te), only_mag=only_mag, rdtype=torch.float64)
+    g64 = torch.autograd.grad((ref64 * T(up).double()).sum(), [p64, m64, v64])
+    gd = torch.autograd.grad((var * dev(up)).sum(), [pv, rm, rv])
+    for k, g_, r_ in zip(("d phi_var", "d R2* mean", "d R2* var"), gd, g64):
+        assert_close(host(g_), r_.numpy(), 2e-5, k)
+
+
 @pytest.mark.parametrize("name", ["pdffu", "pdffu_rem"])
 def test_pdff_uncertainty(golden, name):
     g = golden("tier2")
