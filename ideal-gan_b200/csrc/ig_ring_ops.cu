@@ -522,7 +522,7 @@ template <int NE, bool EXACT> struct PdffUncOp {
         }
         // C = G^-1 = 1/det [[g11, -g01], [-conj(g01), g00]]
         const pk det = vsub(vmul(g00, g11), vfma(g01.re, g01.re, vmul(g01.im, g01.im)));
-        const pk id = mk(1.0f / det.d.x, 1.0f / det.d.y);
+        const pk id = mk(__fdividef(1.0f, det.d.x), __fdividef(1.0f, det.d.y));      // SFU reciprocal (2 ulp); the weights above carry more rounding than that
         const pk c00 = vmul(g11, id), c11 = vmul(g00, id);
         const cx<pk> c01{vneg(vmul(g01.re, id)), vneg(vmul(g01.im, id))};
         const cx<pk> rho_w{vfma(c00, r0.re, vsub(vmul(c01.re, r1.re), vmul(c01.im, r1.im))), vfma(c00, r0.im, vfma(c01.re, r1.im, vmul(c01.im, r1.re)))};
@@ -533,7 +533,10 @@ template <int NE, bool EXACT> struct PdffUncOp {
         st_cx(rho_b, v0, cx<pk>{vmul(inv, rho_w.re), vmul(inv, rho_w.im)});
         st_cx(rho_b + static_cast<size_t>(nv) * 2, v0, cx<pk>{vmul(inv, rho_f.re), vmul(inv, rho_f.im)});
         const pk m01 = vfma(c01.re, c01.re, vmul(c01.im, c01.im));
-        const pk a01 = vmul(inv2, mk(sqrtf(m01.d.x), sqrtf(m01.d.y)));
+        float s0, s1;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(m01.d.x));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(m01.d.y));
+        const pk a01 = vmul(inv2, mk(s0, s1));
         float *cov_b = p.cov + static_cast<size_t>(b) * 4 * nv;
         st_real(cov_b, v0, vmul(inv2, mk(fabsf(c00.d.x), fabsf(c00.d.y))));
         st_real(cov_b + nv, v0, a01);

@@ -191,7 +191,7 @@ template <int NE> __global__ void __launch_bounds__(kThreads) cse_mag_fwd2_kerne
 
 // Adjoint with two voxels per thread and every load issued before the math: the one-voxel kernel below fetched each upstream
 // echo inside the `fit > 1e-6` branch, one dependent 4-byte load after the other (0.535 ms = 35 % of the HBM rate for 128 B/voxel).
-template <int NE> __global__ void __launch_bounds__(kThreads) cse_mag_bwd2_kernel(const CseParams p) {
+template <int NE> __global__ void __launch_bounds__(kThreads, NE <= 8 ? 3 : 2) cse_mag_bwd2_kernel(const CseParams p) {
     __shared__ MagTab<NE> T;
     const int b = blockIdx.y;
     stage_mag_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne);
@@ -225,17 +225,17 @@ template <int NE> __global__ void __launch_bounds__(kThreads) cse_mag_bwd2_kerne
     }
     pk Rnu = zero;
     if (p.r2nu) Rnu = vmul(p.r2_sc * kLog2e, ld_real(p.r2nu + vb, v, pk{}));
-    pk y[NE], wm[NE];
+    pk wm[NE];      // y_e = (wm_e S_e)^2 is re-formed where needed: holding it costs 2 NE registers and a block per SM
     pk a = zero, bb = zero, c = zero;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         if (e < ne) {
             wm[e] = fast_ex2(vmul(T.te[e], R));
             const pk t = vmul(wm[e], S[e]);
-            y[e] = vmul(t, t);
-            a = vfma(T.p0[e], y[e], a);
-            bb = vfma(T.p1[e], y[e], bb);
-            c = vfma(T.p2[e], y[e], c);
+            const pk y = vmul(t, t);
+            a = vfma(T.p0[e], y, a);
+            bb = vfma(T.p1[e], y, bb);
+            c = vfma(T.p2[e], y, c);
         }
     }
     pk ga = zero, gb = zero, gc = zero;
@@ -283,8 +283,9 @@ template <int NE> __global__ void __launch_bounds__(kThreads) cse_mag_bwd2_kerne
                     gy = vadd(gy, Gd[e]);
                 }
             }
-            gS = vfma(vmul(vmul(2.0f, gy), wm[e]), vmul(wm[e], S[e]), gS);
-            gR = vfma(vmul(2.0f * T.te[e], gy), y[e], gR);
+            const pk t = vmul(wm[e], S[e]);
+            gS = vfma(vmul(vmul(2.0f, gy), wm[e]), t, gS);
+            gR = vfma(vmul(2.0f * T.te[e], gy), vmul(t, t), gR);
             if (p.g_mag) st_real(p.g_mag + eb + static_cast<size_t>(e) * nv, v, gS);
         }
     }

@@ -114,8 +114,9 @@ def main():
     add("ig_acq_unc_bwd", "acq_uncertainty adjoint (d phi_var, d R2* mean, d R2* var)", nb, nv, ne, 16 + 12 + 8 * ne + 12,
         lambda: ops.acq_unc_bwd(rho_hat, pv, rm, rv, tab, ne, up_var))
     del up_var
+    phm = pm[..., 0:1].contiguous()
     add("ig_pdff_unc", "PDFF_uncertainty (weighted LS per voxel)", nb, nv, ne, 8 * ne + 16 + 16 + 16,
-        lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab))
+        lambda: ops.pdff_unc(acqs, phm, pv, rm, rv, tab))
     add("ig_pdff_extract", "PDFF map", nb, nv, ne, 16 + 4, lambda: ops.pdff_extract(rho_hat))
     _, _, demod_s, ls_s, _ = ops.cse_mag_fwd(mag, r2map, tab)
     add("ig_mag_regs", "train-IDEAL-mag regularisers (4 sums + gradients)", nb, nv, ne, 2 * (4 * ne + 12 + 4),

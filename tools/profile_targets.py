@@ -30,6 +30,8 @@ mag = torch.sqrt((acqs ** 2).sum(-1, keepdim=True)).contiguous()
 _, _, demod_s, ls_s, _ = ops.cse_mag_fwd(mag, rm.reshape(nb, 1, H, W, 1), tab)
 var5 = torch.rand((nb, 5, H, W, 2), device=dev, generator=g) * 1e-3
 mp3 = mp[..., :3].contiguous()
+ups5 = [torch.randn((nb, c_, H, W, 1), device=dev, generator=g) for c_ in (2, ne, ne, 3, 1)]
+phm = pm[..., 0:1].contiguous()
 targets = [
     lambda: ops.a2a_loss(acqs, pm, tab),
     lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True),
@@ -46,8 +48,11 @@ targets = [
     lambda: ops.ideal_decode(L.MODEL_MAGPHA, mp3, tab, ne),
     lambda: ops.ideal_decode(L.MODEL_MAGPHA, mp3, tab, ne, want_shat=True),
     lambda: ops.pdff_extract(up_rho),
-    lambda: ops.pdff_unc(acqs, pm[..., 0:1].contiguous(), pv, rm, rv, tab),
+    lambda: ops.pdff_unc(acqs, phm, pv, rm, rv, tab),
     lambda: ops.cse_mag_fwd(mag, rm.reshape(nb, 1, H, W, 1), tab),
+    lambda: ops.cse_mag_bwd(mag, rm.reshape(nb, 1, H, W, 1), tab, ups5),
+    lambda: ops.acq_unc_fwd(up_rho, pv, rm, rv, tab, ne),
+    lambda: ops.acq_unc_bwd(up_rho, pv, rm, rv, tab, ne, up),
     lambda: ops.a2a_fwd(acqs, pm, tab),
     lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=False),
 ]
