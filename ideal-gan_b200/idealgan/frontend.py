@@ -72,6 +72,8 @@ def _dispatch(fn, tensors, names, te=None, out_shapes=None):
     """Run `fn(*tensors[, te])` (an idealgan.torch_ops function of torch tensors) on torch / numpy inputs, or lift it to
     TensorFlow when any argument -- the echo times included, which are symbolic inside @tf.function -- is a tf tensor.
     `out_shapes`: static output shapes, needed by the graph-mode hop (tf.py_function loses them)."""
+    if te is not None and tf_ops.tf is not None and tf_ops.is_tf_tensor(te) and not _is_tf(*tensors) and hasattr(te, "numpy"):
+        te = te.numpy()      # torch / numpy data with the session's default echo times (gen_TEvar made a tf constant): stay on the torch route
     consts = [] if te is None else [te]
     if tf_ops.tf is not None and _is_tf(*tensors, *consts):
         return tf_ops.bridge(fn, out_shapes, n_const=len(consts))(*tensors, *consts)
