@@ -343,6 +343,12 @@ extern "C" int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, cons
     if (int rc = check_model_args("ig_ideal_fwd", model, rows_or_ch, nb, ne, nv)) return rc;
     FwdParams p{};
     p.maps = maps_d; p.tab = tab_d; p.out = out_d; p.rows_or_ch = rows_or_ch; p.nb = nb; p.ne = ne; p.nv = nv; p.flags = flags; p.r2_sc = r2_sc;
+    if (flags & IG_F_ONLY_MAG) {
+        // |S_hat| only, (nb, ne, nv): the decode kernel without its clip (half the output bytes; the field-map phasor is never formed)
+        IG_REQUIRE(!(flags & IG_F_FLAT), IG_E_UNSUPPORTED, "ig_ideal_fwd: IG_F_ONLY_MAG comes with the planar layout");
+        p.out = nullptr; p.mag = out_d; p.flags = flags | IG_F_NO_CLIP;
+        return launch_model<MODE_DEC>(model, p, static_cast<cudaStream_t>(stream));
+    }
     return launch_model<MODE_FWD>(model, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -75,9 +75,11 @@ def _model_dims(model, maps):
 
 
 def ideal_fwd(model, maps, tab, ne, r2_sc=200.0, flags=0):
-    """flags & F_FLAT: the result comes out channel-interleaved, (nb, H, W, 2 ne) = data.A_from_MEBCRN(IDEAL_op(maps))."""
+    """flags & F_FLAT: the result comes out channel-interleaved, (nb, H, W, 2 ne) = data.A_from_MEBCRN(IDEAL_op(maps));
+    flags & F_ONLY_MAG: the magnitudes |S_hat| (nb, ne, H, W, 1)."""
     maps, nb, H, W, roc = _model_dims(model, maps)
-    out = torch.empty((nb, H, W, 2 * ne) if flags & L.F_FLAT else (nb, ne, H, W, 2), dtype=torch.float32, device=maps.device)
+    shape = (nb, H, W, 2 * ne) if flags & L.F_FLAT else ((nb, ne, H, W, 1) if flags & L.F_ONLY_MAG else (nb, ne, H, W, 2))
+    out = torch.empty(shape, dtype=torch.float32, device=maps.device)
     L.check(L.load().ig_ideal_fwd(model, maps.data_ptr(), roc, tab.data_ptr(), nb, ne, H * W, float(r2_sc), flags,
                                   out.data_ptr(), _stream()), "ig_ideal_fwd")
     return out

@@ -98,6 +98,8 @@ def ideal_forward(model, maps, te, field=1.5, r2_sc=200.0, flags=0):
     _check_batch(tab.shape[0], maps.shape[0])
     if _no_grad(maps):
         return ops.ideal_fwd(model, maps, tab, ne, float(r2_sc), int(flags))
+    if flags & L.F_ONLY_MAG:
+        raise ValueError("ideal_forward: the magnitude-only output (F_ONLY_MAG) is an inference option; no adjoint kernel takes a magnitude upstream")
     return _IdealForward.apply(maps, tab, model, ne, float(r2_sc), int(flags))
 
 

@@ -63,7 +63,7 @@ enum { IG_MODEL_WFPM = 0, IG_MODEL_FFPD = 1, IG_MODEL_MAGPHA = 2 };
 enum {
     IG_F_PHASE_CONSTRAINT = 1,  /* get_rho(phase_constraint=True)                                 */
     IG_F_FLAT = 2,              /* flat layout (MEBCRN=False)                                     */
-    IG_F_ONLY_MAG = 4,          /* acq_to_acq(only_mag=True): second output is |S_hat|, 1 channel  */
+    IG_F_ONLY_MAG = 4,          /* acq_to_acq(only_mag=True) / ig_ideal_fwd: the signal output is |S_hat|, 1 channel */
     IG_F_NO_RELU = 8,           /* IG_MODEL_WFPM without the relu gate on R2* (not used by wflib) */
     IG_F_NO_CLIP = 16           /* ig_ideal_decode: images as computed, without clip_by_value(., 0, 1) */
 };
@@ -88,7 +88,8 @@ size_t ig_loss_scratch_bytes(int nb, int nv);
 
 /* ---- forward models: IDEAL_model / IDEAL_mag / IDEAL_mag_phase (IDEAL_model.py:220-299,404-509) */
 /* maps_d layout by model (see top); rows_or_ch = rows (WFPM: 3|4, FFPD: 3) or channels (MAGPHA: 3|4).
- * out_d: (nb, ne, nv, 2), or with IG_F_FLAT the channel-interleaved (nb, nv, 2 ne) of data.A_from_MEBCRN (forward only). */
+ * out_d: (nb, ne, nv, 2), or with IG_F_FLAT the channel-interleaved (nb, nv, 2 ne) of data.A_from_MEBCRN (forward only), or with
+ * IG_F_ONLY_MAG the magnitudes |S_hat| (nb, ne, nv) (forward only; what gen_LDM_dataset.py:234 reduces the signals to). */
 int ig_ideal_fwd(int model, const float *maps_d, int rows_or_ch, const float *tab_d, int nb, int ne, int nv,
                  float r2_sc, int flags, float *out_d, void *stream);
 /* The forward model as the dataset-synthesis script consumes it (gen_LDM_dataset.py:156-158,217-235): any of

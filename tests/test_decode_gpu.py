@@ -68,6 +68,22 @@ def test_decode_magpha_vs_oracle(hw, ch):
     assert_close(host(raw), np.sqrt((host(sig_r) ** 2).sum(-1)), TOL, "unclipped magnitudes")
 
 
+@pytest.mark.parametrize("model,maker", [(L.MODEL_WFPM, "wfpm"), (L.MODEL_FFPD, "ffpd"), (L.MODEL_MAGPHA, "magpha")])
+def test_forward_only_mag_flag(model, maker):
+    """ig_ideal_fwd with IG_F_ONLY_MAG: |forward model|, one channel (the forward models' counterpart of acq_to_acq(only_mag=True))."""
+    nb, H, W, ne = 2, 24, 32, 6
+    rng = np.random.default_rng(8)
+    maps = {"wfpm": synth.wfpm_maps, "ffpd": synth.ffpd_maps, "magpha": synth.magpha_maps}[maker](nb, H, W, rng)
+    te = dev(synth.te_orig(nb, ne))
+    tab = ops.gen_tables(te, 1.5)
+    full = ops.ideal_fwd(model, dev(maps), tab, ne)
+    mag = ops.ideal_fwd(model, dev(maps), tab, ne, flags=L.F_ONLY_MAG)
+    assert tuple(mag.shape) == (nb, ne, H, W, 1)
+    assert_close(host(mag[..., 0]), np.sqrt((host(full) ** 2).sum(-1)), TOL, "|S_hat|")
+    with pytest.raises(ValueError):
+        ops.ideal_fwd(model, dev(maps), tab, ne, flags=L.F_ONLY_MAG | L.F_FLAT)
+
+
 @pytest.mark.parametrize("model,maker", [(L.MODEL_WFPM, "wfpm"), (L.MODEL_FFPD, "ffpd")])
 def test_decode_complex_row_models(model, maker):
     nb, H, W, ne = 2, 48, 64, 6
