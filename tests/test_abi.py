@@ -101,3 +101,19 @@ def test_header_is_plain_c(tmp_path):
                    "int probe(void) { ig_peer *p = 0; ig_ctx *c = 0; (void)p; (void)c; return IG_VERSION + IG_E_ARG + (int)sizeof(size_t); }\n")
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                    check=True, capture_output=True, text=True)
+
+
+@pytest.mark.gpu
+def test_c_program_round_trip_without_python_or_torch(tmp_path):
+    """tests/c_abi/roundtrip.c: the library driven from plain C (gcc, cudaMalloc, raw pointers): tables -> forward model ->
+    LS solve gives the water / fat maps back to 1e-5, and bad arguments come back as IG_E_* codes."""
+    import subprocess
+    exe = tmp_path / "roundtrip"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "roundtrip.c"), "-L", libdir, "-lidealgan", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                    "-o", str(exe)], check=True, capture_output=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and "C ABI round trip ok" in out.stdout, out.stdout + out.stderr
