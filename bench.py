@@ -363,6 +363,24 @@ def configs_leg(device, peak, reps):
                  "voxel_echoes_per_s": nvox3 * NE / ((t_f + t_s + t_b) * 1e-3)}
     del acqs3, pm3, maps3, up_rho
 
+    # ---- the published model's own objectives on the C2 batch (train-IDEAL-unsup.py:214-231 UQ stage, :267-292 R2* stage) -------------
+    acqs2, pm2, te2d, _ = build_device_inputs(device, 1234)
+    tab2 = ops.gen_tables(te2d, FIELD)
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    pv = torch.rand((NB, 1, H, W, 1), device=device, generator=g) * 4e-3
+    rv = torch.rand((NB, 1, H, W, 1), device=device, generator=g) * 3e-3
+    rm = pm2[..., 1:2].contiguous()
+    t_uq = float(np.median(event_times(lambda: ops.a2a_uq_loss(acqs2, pm2, pv, rm, rv, tab2), reps)))
+    t_ri = float(np.median(event_times(lambda: ops.a2a_rician_loss(acqs2, pm2, pv, rm, rv, tab2), reps)))
+    out["C2_uncertainty_objectives"] = {
+        "what": "acq_to_acq + acq_uncertainty(stop_gradient) + VarMeanSquaredError (ig_a2a_uq_loss) and its Rician R2*-stage twin (ig_a2a_rician_loss): "
+                "loss + all gradients in one kernel each, 64 x 384 x 384 x 6, 88 algorithmic bytes per voxel",
+        "uq_ms": t_uq, "uq_frac": frac(88, NB * H * W, t_uq), "uq_voxel_echoes_per_s": NB * H * W * NE / (t_uq * 1e-3),
+        "rician_ms": t_ri, "rician_frac": frac(88, NB * H * W, t_ri), "rician_voxel_echoes_per_s": NB * H * W * NE / (t_ri * 1e-3),
+        "note": "both are bound by instruction issue, not by HBM (DESIGN.md 4.2, profiles/ncu_kernels_r02.md)"}
+    del acqs2, pm2, pv, rv, rm
+
     # ---- C4: bipolar mag/phase self-supervised objective (train-IDEAL-single.py:154-157,175) -----------------------------
     def c4_batch(nb):
         te = synth.te_random(nb, NE, rng, te_ini_d=0.4e-3, d_te_min=1.0e-3, d_te_d=0.3e-3)

@@ -422,13 +422,14 @@ struct UncParams {
 
 // V = pk: two neighbouring voxels per thread (16-byte loads of rho, 8-byte loads of the moment maps, 16- or 8-byte stores per echo);
 // V = float: odd voxel counts / unaligned planes.  (One voxel per thread with 4- and 8-byte accesses measured 88 % / 74 % of the HBM rate.)
-template <int NE, bool BWD, typename V> __global__ void __launch_bounds__(kThreads) acq_unc_kernel(const UncParams p) {
+template <int NE, bool BWD, typename V, int CH> __global__ void __launch_bounds__(kThreads) acq_unc_kernel(const UncParams p) {
     __shared__ SampleTab<NE> T;
     const int b = blockIdx.y;
     stage_table(T, p.tab + static_cast<size_t>(b) * IG_TAB_FLOATS, p.ne, 1.0f);
     const int v = (blockIdx.x * blockDim.x + threadIdx.x) * lanes<V>::n;
     if (v >= p.nv) return;
-    const int nv = p.nv, ne = p.ne, ch = p.ch;
+    const int nv = p.nv, ne = p.ne;
+    constexpr int ch = CH;                      // compile-time: a run-time channel count predicated every upstream load and serialised them
     const size_t vb = static_cast<size_t>(b) * nv;
     const V zero = splat<V>(0.f);
     const float *rho_b = p.rho + static_cast<size_t>(b) * 2 * nv * 2;
@@ -441,17 +442,20 @@ template <int NE, bool BWD, typename V> __global__ void __launch_bounds__(kThrea
     V g_sphi = zero, g_mu = zero, g_sr = zero;
     [[maybe_unused]] V G[NE];
     if constexpr (BWD) {
+        // every upstream load in flight before the first is consumed
+        [[maybe_unused]] cx<V> G2[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             if (e < ne) {
                 const float *g_e = p.g_out + (static_cast<size_t>(b) * ne + e) * nv * ch;
-                if (ch == 2) {
-                    const cx<V> g2 = ld_cx(g_e, v, V{});
-                    G[e] = vadd(g2.re, g2.im);
-                } else {
-                    G[e] = ld_real(g_e, v, V{});
-                }
+                if constexpr (ch == 2) G2[e] = ld_cx(g_e, v, V{});
+                else G[e] = ld_real(g_e, v, V{});
             }
+        }
+        if constexpr (ch == 2) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (e < ne) G[e] = vadd(G2[e].re, G2[e].im);
         }
     }
 #pragma unroll
@@ -465,7 +469,7 @@ template <int NE, bool BWD, typename V> __global__ void __launch_bounds__(kThrea
             if constexpr (!BWD) {
                 const V var = vmul(vfma(er, s_r, vsub(splat<V>(1.0f), ephi)), a2);        // 1 - e^{-x} literally, as the reference forms it
                 float *o_e = p.out + (static_cast<size_t>(b) * ne + e) * nv * ch;
-                if (ch == 2) st_cx(o_e, v, cx<V>{var, var});
+                if constexpr (ch == 2) st_cx(o_e, v, cx<V>{var, var});
                 else st_real(o_e, v, var);
             } else {
                 const V g = vmul(G[e], a2);
@@ -679,9 +683,11 @@ extern "C" int ig_acq_unc_fwd(const float *rho_d, const float *phi_var_d, const 
         constexpr int NE = decltype(ne_c)::value;
         auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
         if (nv % 2 == 0 && aligned16(rho_d) && al8(phi_var_d) && al8(r2_mean_d) && al8(r2_var_d) && (only_mag ? al8(out_d) : aligned16(out_d)))
-            acq_unc_kernel<NE, false, pk><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+            only_mag ? acq_unc_kernel<NE, false, pk, 1><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p)
+                     : acq_unc_kernel<NE, false, pk, 2><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         else
-            acq_unc_kernel<NE, false, float><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+            only_mag ? acq_unc_kernel<NE, false, float, 1><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p)
+                     : acq_unc_kernel<NE, false, float, 2><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         IG_CUDA(cudaGetLastError());
         return 0;
     });
@@ -701,9 +707,11 @@ extern "C" int ig_acq_unc_bwd(const float *rho_d, const float *phi_var_d, const 
         auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
         if (nv % 2 == 0 && aligned16(rho_d) && al8(phi_var_d) && al8(r2_mean_d) && al8(r2_var_d) && (only_mag ? al8(g_out_d) : aligned16(g_out_d)) &&
             al8(g_phi_var_d) && al8(g_r2_mean_d) && al8(g_r2_var_d))
-            acq_unc_kernel<NE, true, pk><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+            only_mag ? acq_unc_kernel<NE, true, pk, 1><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p)
+                     : acq_unc_kernel<NE, true, pk, 2><<<grid_for(nb, nv, 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         else
-            acq_unc_kernel<NE, true, float><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+            only_mag ? acq_unc_kernel<NE, true, float, 1><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p)
+                     : acq_unc_kernel<NE, true, float, 2><<<grid_for(nb, nv, 1), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
         IG_CUDA(cudaGetLastError());
         return 0;
     });
