@@ -21,6 +21,11 @@ class _TableCache:
         self.hits = self.misses = 0
 
     def get(self, te, field, device):
+        if torch.cuda.is_current_stream_capturing():
+            # Inside a CUDA-graph capture the table is part of the captured step: it is rebuilt by every replay from whatever the echo-time
+            # buffer holds then.  A cached table would be baked into the graph (stale after the buffer is refilled), and one built here
+            # lives in the graph's private pool, so nothing is looked up and nothing is stored.
+            return ops.gen_tables(te.to(device).contiguous(), field)
         stream = torch._C._cuda_getCurrentRawStream(device.index)     # a table is ordered on the stream that built it
         if te.is_cuda:
             key = ("dev", te.data_ptr(), te._version, tuple(te.shape), te.stride(), float(field), device.index, stream)

@@ -68,3 +68,36 @@ def test_captured_step_replays_with_new_data(objective):
         ref_l, ref_g = step()
         np.testing.assert_allclose(got_l.item(), ref_l.item(), rtol=1e-6)
         assert torch.equal(got_g, ref_g)
+
+
+def test_drop_in_call_captured_in_a_graph_rebuilds_its_table_on_replay():
+    """`wf.*` calls cache the per-sample table per echo train -- but not inside a capture: the table belongs to the captured step and
+    must follow the echo-time buffer on every replay (a cached one would be baked into the graph; one built inside the capture lives
+    in the graph's private pool and may not be handed to later eager calls)."""
+    import wflib as wf
+    from idealgan import torch_ops as TO
+    nb, H, W, ne = 2, 32, 48, 6
+    maps, te2d = _data(nb, H, W, ne, 10)
+    te = te2d[:, :, None].contiguous()
+    tab = ops.gen_tables(te, 1.5)
+    acqs = ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne)
+    pm = maps[:, 2:3].contiguous()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            wf.get_rho(acqs, pm, te=te)                        # eager warm-up: this DOES cache a table for (te, version)
+    torch.cuda.current_stream().wait_stream(side)
+    cached = len(TO.table_cache.entries)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        rho_g = wf.get_rho(acqs, pm, te=te)
+    assert len(TO.table_cache.entries) == cached               # nothing stored from inside the capture
+    for seed in (11, 12):
+        m2, t2 = _data(nb, H, W, ne, seed)
+        te.copy_(t2[:, :, None])                               # new echo trains in the same buffer
+        acqs.copy_(ops.ideal_fwd(L.MODEL_WFPM, m2, ops.gen_tables(te, 1.5), ne))
+        pm.copy_(m2[:, 2:3])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(rho_g, wf.get_rho(acqs, pm, te=te)), "the captured step used a stale table"
