@@ -274,6 +274,11 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
             // measured at 64 x 384 x 384 x 6: the grid + finish pair wins for the complex-row models (0.159 vs 0.165 ms), the
             // persistent kernel for mag/phase, whose 128 registers leave too few warps for the one-tile-per-block shape (0.213 vs 0.251 ms)
             if (MODEL != IG_MODEL_MAGPHA) {
+                if (packed) {      // 128-voxel rows, <= 8 echoes, <= 4 map rows: the TMA ring (ig_ring_ops.cu, RowLossOp)
+                    const int rc = row_loss_ring(MODEL, p.maps, p.rows_or_ch, p.acqs, p.tab, p.nb, p.ne, p.nv, p.r2_sc, p.flags, p.inv_n, p.gmaps, p.out, p.loss,
+                                                 p.scratch, st);
+                    if (rc != IG_E_UNSUPPORTED) return rc;
+                }
                 const dim3 g = grid_for(p.nb, p.nv, packed ? 2 : 1);
                 if (packed) ideal_loss_grid_kernel<NE, pk, MODEL><<<g, kThreads, 0, st>>>(p);
                 else ideal_loss_grid_kernel<NE, float, MODEL><<<g, kThreads, 0, st>>>(p);

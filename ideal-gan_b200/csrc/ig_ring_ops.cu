@@ -265,6 +265,128 @@ int magpha_loss_ring(const float *maps, const float *acqs, const float *tab, int
 }
 
 // =================================================================================================
+// the same fused objective for the complex-row parameterisations (WF-PM maps with 3 or 4 rows, ff/pd/phase maps): the rows are
+// planes of (Re, Im) pairs like the echoes, so one tensor map with `rows` planes delivers them (math: ideal_voxels<MODE_LOSS>)
+// =================================================================================================
+struct RowLossParams {
+    const float *maps, *acqs, *tab;
+    float *gmaps, *shat, *loss;
+    void *scratch;
+    int nb, ne, nv, tile_stride, rows, flags;
+    float r2_sc, inv_n;
+};
+
+template <int MODEL, int NE, bool EXACT> struct RowLossOp {
+    using Params = RowLossParams;
+    struct Shared {};
+    static constexpr int kNE = NE, kMaps = 2;
+    static constexpr bool kExact = EXACT, kDynamic = true, kLoss = true, kWritesStage = false;
+    static constexpr int fpv(int) { return 2; }
+    static constexpr int planes_max(int m) { return m == 0 ? 4 : NE; }
+    static constexpr int kStageBytes = (4 + NE) * kRingTileVox * 8 + ((NE * 64 + 127) / 128) * 128;
+    static constexpr int kStages = 2 * 3 * kStageBytes <= kRingSmemBudget ? 3 : 2, kMinBlocks = 2;
+    __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? p.rows : ne; }
+    __device__ static void prologue(Shared &) {}
+
+    __device__ static __forceinline__ void chunk(const Params &p, Shared &, unsigned char *stage, const SampleTab<NE> &T, int slot, int b, int v0,
+                                                 bool active, int ne, float &loss_part) {
+        using Lay = RingLayout<RowLossOp>;
+        const float4 *sA = reinterpret_cast<const float4 *>(stage + Lay::off(1)) + slot;
+        const float4 *sM = reinterpret_cast<const float4 *>(stage + Lay::off(0)) + slot;
+        const int nv = p.nv, rows = p.rows;
+        float *g_b = p.gmaps + static_cast<size_t>(b) * rows * nv * 2;
+        const pk zero = splat<pk>(0.f);
+        // background chunk (every measured component zero): the mask removes every residual -> loss 0, gradient 0
+        bool nz = false;
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (EXACT || e < ne) nz = nz || !all_zero(sA[e * kPlaneF4]);
+        }
+        if (!__any_sync(0xffffffffu, nz) && !p.shat) {
+            if (active)
+                for (int r = 0; r < rows; ++r) st_row<pk>(g_b, r, nv, v0, czero<pk>());
+            return;
+        }
+        if (!active) return;
+        auto row = [&](int r) { const float4 q = sM[r * kPlaneF4]; return cx<pk>{mk(q.x, q.z), mk(q.y, q.w)}; };
+        Voxel<pk> x;
+        x.bturn = zero; x.ff = zero; x.pd = zero; x.uW = czero<pk>(); x.uF = czero<pk>();
+        const cx<pk> m0 = row(0), m1 = row(1), m2 = row(2);
+        if constexpr (MODEL == IG_MODEL_WFPM) {
+            x.rhoW = cx<pk>{vmul(kRhoSc, m0.re), vmul(kRhoSc, m0.im)};
+            x.rhoF = cx<pk>{vmul(kRhoSc, m1.re), vmul(kRhoSc, m1.im)};
+            x.phi_t = m2.re;
+            x.r2raw = m2.im;
+            x.r2 = (p.flags & IG_F_NO_RELU) ? m2.im : vrelu(m2.im);
+            if (rows > 3) x.bturn = vmul(0.5f, row(rows - 1).re);
+        } else {
+            x.ff = m0.re;
+            x.pd = m1.re;
+            x.r2raw = x.r2 = m1.im;
+            x.phi_t = m2.im;
+            unit_phasor(vmul(2.0f, m2.re), x.uW.re, x.uW.im);
+            const pk aa = vmul(kRhoSc, x.pd);
+            x.rhoW = cscale(vfma(vneg(aa), x.ff, aa), x.uW);
+            x.rhoF = cscale(vmul(aa, x.ff), x.uW);
+        }
+        const pk r2s = vmul(p.r2_sc, x.r2);                               // the stage carries the unscaled decay constant
+        Adj<pk> a;
+        a.sg = czero<pk>(); a.sgc = czero<pk>(); a.tq = czero<pk>(); a.q = czero<pk>(); a.bq = zero;
+        pk lsum = zero;
+        const size_t acq_b = static_cast<size_t>(b) * ne * nv * 2;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (EXACT || e < ne) {
+                const EchoRec R = T.r[e];
+                pk c, s;
+                unit_phasor(vfma(R.sgn, x.bturn, vmul(R.kphi, x.phi_t)), c, s);
+                const pk d = fast_ex2(vmul(R.kdec, r2s));
+                const cx<pk> w{vmul(d, c), vmul(d, s)};
+                const cx<pk> yhat = caffine(x.rhoW, R.c_re, R.c_im, x.rhoF);
+                const cx<pk> shat = cmulv(w, yhat);
+                const float4 A = sA[e * kPlaneF4];
+                const cx<pk> G{mask_sub(shat.re, mk(A.x, A.z)), mask_sub(shat.im, mk(A.y, A.w))};
+                lsum = vfma(G.re, G.re, lsum);
+                lsum = vfma(G.im, G.im, lsum);
+                if (p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                const cx<pk> g = cmulc(w, G);
+                a.sg.re = vadd(a.sg.re, g.re);
+                a.sg.im = vadd(a.sg.im, g.im);
+                cmac(a.sgc, R.c_re, -R.c_im, g);
+                const cx<pk> q = cmulc(g, yhat);
+                a.tq.re = vfma(R.te, q.re, a.tq.re);
+                a.tq.im = vfma(R.te, q.im, a.tq.im);
+                if constexpr (MODEL == IG_MODEL_FFPD) { a.q.re = vadd(a.q.re, q.re); a.q.im = vadd(a.q.im, q.im); }
+                else a.bq = vfma(R.sgn, q.im, a.bq);
+            }
+        }
+        loss_part += hsum(lsum);
+        write_grads<pk, MODEL>(g_b, rows, nv, v0, p.flags, x, a, p.r2_sc, 2.0f * p.inv_n);
+    }
+};
+
+int row_loss_ring(int model, const float *maps, int rows, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float inv_n,
+                  float *gmaps, float *shat, float *loss, void *scratch, cudaStream_t st) {
+    if (ne > 8 || rows > 4 || nv % 128 != 0 || !aligned16(gmaps) || (shat && !aligned16(shat)) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24))
+        return IG_E_UNSUPPORTED;
+    RowLossParams p{};
+    p.maps = maps; p.acqs = acqs; p.tab = tab; p.gmaps = gmaps; p.shat = shat; p.loss = loss; p.scratch = scratch;
+    p.nb = nb; p.ne = ne; p.nv = nv; p.rows = rows; p.flags = flags; p.r2_sc = r2_sc; p.inv_n = inv_n;
+    RingMaps m{};
+    if (!ring_tensor_map(&m.m[0], maps, nv, 2, static_cast<long>(nb) * rows, static_cast<long>(nv) * 2, rows)) return IG_E_UNSUPPORTED;
+    if (!ring_tensor_map(&m.m[1], acqs, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
+    auto go = [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (model == IG_MODEL_WFPM) return ne == NE ? ring_launch<RowLossOp<IG_MODEL_WFPM, NE, true>>(p, m, st) : ring_launch<RowLossOp<IG_MODEL_WFPM, NE, false>>(p, m, st);
+        return ne == NE ? ring_launch<RowLossOp<IG_MODEL_FFPD, NE, true>>(p, m, st) : ring_launch<RowLossOp<IG_MODEL_FFPD, NE, false>>(p, m, st);
+    };
+    if (ne <= 4) return go(std::integral_constant<int, 4>{});
+    if (ne <= 6) return go(std::integral_constant<int, 6>{});
+    return go(std::integral_constant<int, 8>{});
+}
+
+// =================================================================================================
 // Rician objective of the R2* stage (math: ig_uq.cu, a2a_rician_loss_kernel, packed lanes)
 // =================================================================================================
 struct RicianParams {

@@ -133,3 +133,33 @@ def test_pdff_uncertainty_ring_vs_plain_kernel_and_fp64_oracle(shape, rem):
         assert_close(got_cov.cpu().numpy(), cov64.numpy(), tol_cov, f"cov ({name} kernel) vs fp64 oracle")
     assert_close(rho.cpu().numpy(), rho_p.cpu().numpy(), 2 * tol_rho, "rho ring vs plain")
     assert_close(cov.cpu().numpy(), cov_p.cpu().numpy(), 2 * tol_cov, "cov ring vs plain")
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 16, 6), (2, 40, 48, 5), (1, 384, 384, 6), (2, 64, 96, 8), (2, 64, 64, 3)])
+@pytest.mark.parametrize("model,rows", [(L.MODEL_WFPM, 3), (L.MODEL_WFPM, 4), (L.MODEL_FFPD, 3)], ids=["wfpm", "wfpm-bipolar", "ffpd"])
+def test_forward_objective_of_the_complex_row_models_ring_vs_plain_kernel(shape, model, rows):
+    """ig_ideal_loss for WF-PM (3 rows, 4 rows with the bipolar one) and ff/pd/phase maps on the generic ring (128-voxel rows, <= 8
+    echoes) against the plain kernels (forced by measurements that start 8 bytes into an allocation), loss, gradient and S_hat."""
+    nb, H, W, ne = shape
+    rng = np.random.default_rng(5 + nb + ne + rows)
+    maps_np = synth.ffpd_maps(nb, H, W, rng) if model == L.MODEL_FFPD else synth.wfpm_maps(nb, H, W, rng, bipolar=(rows == 4))
+    maps = torch.from_numpy(maps_np).cuda()
+    te = torch.from_numpy(synth.te_random(nb, ne, rng)).cuda()
+    tab = ops.gen_tables(te, 1.5)
+    sig = ops.ideal_fwd(model, maps, tab, ne)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acqs = torch.where(sig != 0, sig + 0.02 * torch.randn(sig.shape, device="cuda", generator=g), torch.zeros_like(sig)).contiguous()
+    acqs[0, 0, H // 2, W // 2, 1] = 0.0                                  # a voxel with one masked component
+    est = (maps * 0.97).contiguous()
+    loss, gmaps, shat = ops.ideal_loss(model, est, acqs, tab, want_shat=True)
+    buf = torch.empty(acqs.numel() + 2, device="cuda")
+    a_off = buf[2:].view_as(acqs)
+    a_off.copy_(acqs)
+    assert a_off.data_ptr() % 16 == 8
+    loss_p, gmaps_p, shat_p = ops.ideal_loss(model, est, a_off, tab, want_shat=True)
+    assert abs(loss.item() - loss_p.item()) <= 2e-6 * abs(loss_p.item())
+    assert_close(gmaps.cpu().numpy(), gmaps_p.cpu().numpy(), 5e-6, "gradient ring vs plain")
+    assert_close(shat.cpu().numpy(), shat_p.cpu().numpy(), 2e-6, "S_hat ring vs plain")
+    loss2, gmaps2, _ = ops.ideal_loss(model, est, acqs, tab)              # without S_hat: background chunks take the zero-fill shortcut
+    assert abs(loss2.item() - loss_p.item()) <= 2e-6 * abs(loss_p.item())
+    assert_close(gmaps2.cpu().numpy(), gmaps_p.cpu().numpy(), 5e-6, "gradient (no S_hat) ring vs plain")
