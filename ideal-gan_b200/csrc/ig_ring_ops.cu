@@ -43,7 +43,10 @@ template <int NE, bool EXACT, bool DS> struct A2aBwdOp {
     static constexpr int planes_max(int m) { return m < 2 ? NE : 1; }
     static constexpr int kStageBytes = (2 * NE + 1) * kRingTileVox * 8 + ((NE * 64 + 127) / 128) * 128;
     static constexpr bool kTwoBlocks = 2 * 2 * kStageBytes <= kRingSmemBudget;
-    static constexpr int kStages = (kTwoBlocks && 2 * 3 * kStageBytes > kRingSmemBudget) ? 2 : 3, kMinBlocks = kTwoBlocks ? 2 : 1;
+    // two blocks per SM with three (or two) stages each where they fit; one block with as many stages as fit otherwise (ne = 9..12: two)
+    static constexpr int kStages = kTwoBlocks ? (2 * 3 * kStageBytes > kRingSmemBudget ? 2 : 3) : (3 * kStageBytes <= kRingSmemBudget ? 3 : 2);
+    static constexpr int kMinBlocks = kTwoBlocks ? 2 : 1;
+    static_assert(kStages * kStageBytes <= kRingSmemBudget, "the ring needs at least two stages in shared memory");
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : (m == 1 ? (p.g_shat ? ne : 0) : 1); }
     __device__ static void prologue(Shared &) {}
 
@@ -135,7 +138,7 @@ template <class Op> static int launch_bwd(const A2aBwdParams &p, cudaStream_t st
 
 int a2a_bwd_ring(const float *acqs, const float *pm, long pm_bstride, const float *tab, int nb, int ne, int nv, float r2_sc, const float *g_rho,
                  const float *g_shat, float *g_acqs, float *g_pm, cudaStream_t st) {
-    if (ne > 8 || nv % 128 != 0 || !aligned16(g_pm) || (g_acqs && !aligned16(g_acqs)) || (g_rho && !aligned16(g_rho))) return IG_E_UNSUPPORTED;
+    if (ne > 12 || nv % 128 != 0 || !aligned16(g_pm) || (g_acqs && !aligned16(g_acqs)) || (g_rho && !aligned16(g_rho))) return IG_E_UNSUPPORTED;
     A2aBwdParams p{};
     p.acqs = acqs; p.pm = pm; p.pm_bstride = pm_bstride; p.tab = tab; p.g_rho = g_rho; p.g_shat = g_shat; p.g_acqs = g_acqs; p.g_pm = g_pm;
     p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
@@ -146,7 +149,8 @@ int a2a_bwd_ring(const float *acqs, const float *pm, long pm_bstride, const floa
     };
     if (ne <= 4) return go(std::integral_constant<int, 4>{});
     if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    return go(std::integral_constant<int, 8>{});
+    if (ne <= 8) return go(std::integral_constant<int, 8>{});
+    return go(std::integral_constant<int, 12>{});      // 9..12 echoes (train-IDEAL-TEaug.py:614-618): 100 KB stages, one block per SM, two stages
 }
 
 // =================================================================================================

@@ -215,7 +215,7 @@ def main():
     add("ig_get_rho_fwd", "ne = 12 LS solve", nb, nv, ne12, 8 * ne12 + 8 + 16, lambda: ops.get_rho_fwd(acqs, pm, tab))
     add("ig_a2a_loss", "ne = 12 C2 fused objective (ring, y parked in the stage)", nb, nv, ne12, 8 * ne12 + 8 + 8, lambda: ops.a2a_loss(acqs, pm, tab))
     up12 = torch.randn_like(acqs)
-    add("ig_a2a_bwd", "ne = 12 acq_to_acq adjoint (dPM only; plain kernel)", nb, nv, ne12, 8 * ne12 + 8 + 8 * ne12 + 8,
+    add("ig_a2a_bwd", "ne = 12 acq_to_acq adjoint (dPM only; generic ring, one block per SM, two 100 KB stages)", nb, nv, ne12, 8 * ne12 + 8 + 8 * ne12 + 8,
         lambda: ops.a2a_bwd(acqs, pm, tab, None, up12, need_acqs=False))
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
