@@ -33,3 +33,36 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = _run("--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr
+
+
+def test_gpu_arm_prints_the_contract_line():
+    """One short run of the GPU arm: exactly one JSON line on stdout with the keys the driver and the judge read."""
+    import pytest
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = _run("--steps", "6", "--warmup", "3", "--e2e-steps", "3", "--c5-slices", "64", "--no-cpu-baseline")
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["metric"] == "voxel-echoes/sec (fwd+bwd)" and d["unit"] == "voxel-echoes/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 6 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "f32" and d["vs_baseline"] is None
+    assert d["value"] > 1e11 and d["ms_per_step"] > 0 and d["gpu_launches"] == 12
+    assert "C2" in d["config"]["workload"] and "model" not in d["config"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 5e8 and e["d2h_bytes_per_step"] > 7e7
+    assert e["host_ceiling"]["h2d_gbs_sum_over_ranks"] > 1 and 0.3 < e["frac_of_host_ceiling"] < 1.5
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.3 < rf["frac"] < 1.05
+    assert 0.3 < rf["frac_unmasked"] <= rf["frac"] + 0.02 and rf["traffic"] and "static" in rf["traffic_source"]
+    assert rf["kernel_ms"] <= d["ms_per_step"] * 1.02
+    assert d["dropin"]["ms_per_step"] > d["dropin"]["one_line_edit"]["ms_per_step"] > 0
+    cfg = d["configs"]
+    assert set(("C1", "C3", "C4", "C5", "C2_uncertainty_objectives")) <= set(cfg)
+    assert cfg["C1"]["graph_latency_us"] < cfg["C1"]["latency_us"] and cfg["C5"]["slices"] == 64 and cfg["C5"]["bytes_d2h"] < cfg["C5"]["bytes_d2h_before_epilogue"]
+    assert 0.5 < cfg["C3"]["forward_frac"] < 1.1 and 0.5 < cfg["C4"]["nb64_frac"] < 1.1
+
+
+test_gpu_arm_prints_the_contract_line = __import__("pytest").mark.gpu(test_gpu_arm_prints_the_contract_line)
