@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(cons
         uint32_t tx = Lay::tab_bytes;
 #pragma unroll
         for (int m = 0; m < Op::kMaps; ++m) tx += static_cast<uint32_t>(Op::planes(m, ne, p)) * Lay::plane_bytes(m);
+        bool released = false;
         for (int it = 0;; ++it) {
             const int s = it % STAGES;
             int k;
@@ -90,6 +91,10 @@ __global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(cons
             else k = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
             const bool end = k >= total;
             if (Op::kDynamic && lane == 0 && !end) k_nxt = claim_async();
+            if (!released && 2 * k >= total) {      // PDL: past the middle of the work a dependent may be scheduled (see a2a_loss_tma_kernel)
+                released = true;
+                if (lane == 0) grid_launch_dependents();
+            }
             const int b = end ? -1 : k / tiles_ps;
             const int j = k - b * tiles_ps;
             const int tile = end ? 0 : static_cast<int>((static_cast<unsigned>(j) * static_cast<unsigned>(p.tile_stride)) % static_cast<unsigned>(tiles_ps));

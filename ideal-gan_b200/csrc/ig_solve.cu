@@ -707,11 +707,20 @@ a2a_loss_tma_kernel(const SolveParams p, const __grid_constant__ CUtensorMap map
         float k_nxt = 0.f;
         if (lane == 0) k_nxt = claim_async();
         int ends_left = (NCW + CH - 1) / CH;
+        bool released = false;
         for (int it = 0;; ++it) {
             const int s = it % STAGES;
             const int k = static_cast<int>(__shfl_sync(0xffffffffu, k_nxt, 0));
             const bool end = k >= total;
             if (lane == 0 && !end) k_nxt = claim_async();
+            // Past the middle of the work, whatever is launched behind this kernel with PDL (the next step's table, the next objective) may be
+            // scheduled as SM resources allow: a small table kernel runs next to our blocks, the blocks of a following objective take our
+            // blocks' place as they exit and run their prologue under our tail.  Every such kernel waits for our completion before it touches
+            // global memory (grid_dependency_wait here / in ig_ring.cuh; ig_gen_tables_ahead by contract).
+            if (!released && 2 * k >= total) {
+                released = true;
+                if (lane == 0) grid_launch_dependents();
+            }
             // Tiles of a sample are visited in a strided order so that cheap background tiles (load-bound) and tissue
             // tiles (math-bound) are in flight together chip-wide instead of in alternating phases.
             const int b = end ? -1 : k / tiles_ps;

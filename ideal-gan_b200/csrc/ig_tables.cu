@@ -142,11 +142,20 @@ __device__ __forceinline__ double half_warp_sum(double v) {
 // device: one warp per sample.  Lane l works on echo l & 15; the two half-warps split the six fat peaks (the
 // 36 fp64 sincos of a 6-echo sample are what the table costs), sums over echoes are half-warp shuffles, and each
 // of the 320 floats of the table is written exactly once.
+//
+// AHEAD (ig_gen_tables_ahead): the launch carries the programmatic-dependent-launch attribute, so the warps start while the kernel in
+// front of them in the stream is still running (one warp per block: it fits next to two resident blocks of a fused objective), build a
+// table that kernel does not touch, and only then wait for it: a kernel launched behind the table therefore still sees everything
+// before it in the stream complete, and pays nothing for the table.
 constexpr int kTabWarps = 4;
-__global__ void __launch_bounds__(kTabWarps * 32) gen_tables_kernel(const float *__restrict__ te, int nb, int ne, float field, float *__restrict__ tab) {
+template <int WARPS, bool AHEAD>
+__global__ void __launch_bounds__(WARPS * 32) gen_tables_kernel(const float *__restrict__ te, int nb, int ne, float field, float *__restrict__ tab) {
     grid_launch_dependents();          // a kernel launched behind this one with PDL may start its prologue now; it still waits for our writes
-    const int b = blockIdx.x * kTabWarps + (threadIdx.x >> 5);
-    if (b >= nb) return;
+    const int b = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= nb) {
+        if (AHEAD) grid_dependency_wait();
+        return;
+    }
     const int lane = threadIdx.x & 31, e = lane & 15, half = lane >> 4;
     const bool live = e < ne;
     const float te_e = live ? te[static_cast<size_t>(b) * ne + e] : 0.f;
@@ -179,6 +188,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) gen_tables_kernel(const float 
         for (int i = 0; i < 3; ++i) tab_b[IG_TAB_AP_OFF + i * IG_MAX_NE + e] = ap[i];
         tab_b[IG_TAB_META_OFF + e] = e == 0 ? static_cast<float>(ne) : (e == 1 ? field : 0.f);
     }
+    if (AHEAD) grid_dependency_wait();     // completion of this grid implies completion of the one in front of it
 }
 
 }  // namespace ig
@@ -186,8 +196,24 @@ __global__ void __launch_bounds__(kTabWarps * 32) gen_tables_kernel(const float 
 extern "C" int ig_gen_tables(const float *te_d, int nb, int ne, float field, float *tab_d, void *stream) {
     IG_REQUIRE(te_d && tab_d && nb > 0, IG_E_ARG, "ig_gen_tables: null pointer or nb <= 0");
     IG_REQUIRE(ne >= 1 && ne <= IG_MAX_NE, IG_E_NE, "ig_gen_tables: ne=%d outside [1, %d]", ne, IG_MAX_NE);
-    ig::gen_tables_kernel<<<(nb + ig::kTabWarps - 1) / ig::kTabWarps, ig::kTabWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(te_d, nb, ne, field, tab_d);
+    ig::gen_tables_kernel<ig::kTabWarps, false><<<(nb + ig::kTabWarps - 1) / ig::kTabWarps, ig::kTabWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(te_d, nb, ne, field, tab_d);
     IG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ig_gen_tables_ahead(const float *te_d, int nb, int ne, float field, float *tab_d, void *stream) {
+    IG_REQUIRE(te_d && tab_d && nb > 0, IG_E_ARG, "ig_gen_tables_ahead: null pointer or nb <= 0");
+    IG_REQUIRE(ne >= 1 && ne <= IG_MAX_NE, IG_E_NE, "ig_gen_tables_ahead: ne=%d outside [1, %d]", ne, IG_MAX_NE);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(nb));
+    cfg.blockDim = dim3(32);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    IG_CUDA(cudaLaunchKernelEx(&cfg, ig::gen_tables_kernel<1, true>, te_d, nb, ne, field, tab_d));
     return 0;
 }
 

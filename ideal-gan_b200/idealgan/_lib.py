@@ -41,6 +41,7 @@ SIGNATURES = {
     "ig_last_error": (C.c_char_p, []),
     "ig_device_ok": (_i, []),
     "ig_gen_tables": (_i, [_fp, _i, _i, _f, _fp, _fp]),
+    "ig_gen_tables_ahead": (_i, [_fp, _i, _i, _f, _fp, _fp]),
     "ig_gen_tables_host": (_i, [_fp, _i, _i, _f, _fp]),
     "ig_loss_scratch_bytes": (_sz, [_i, _i]),
     "ig_ideal_fwd": (_i, [_i, _fp, _i, _fp, _i, _i, _i, _f, _i, _fp, _fp]),

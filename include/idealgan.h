@@ -78,6 +78,11 @@ int ig_device_ok(void);
 /* ---- per-sample tables: gen_M / gen_A (IDEAL_model.py:48-97) --------------------------------- */
 /* te_d: (nb, ne) seconds -> tab_d: (nb, IG_TAB_FLOATS).  Arithmetic in fp64, stored fp32. */
 int ig_gen_tables(const float *te_d, int nb, int ne, float field, float *tab_d, void *stream);
+/* The same table, built AHEAD of its use in a training loop: the launch overlaps the kernel in front of it in `stream` (programmatic
+ * dependent launch) instead of waiting for it, and completes only after that kernel has.  The caller promises that te_d was complete
+ * before that kernel was launched and that tab_d is neither read nor written by it (e.g. three table buffers in rotation: step i
+ * launches the table of batch i + 1, then the objective of batch i).  Work launched behind this call is ordered as usual. */
+int ig_gen_tables_ahead(const float *te_d, int nb, int ne, float field, float *tab_d, void *stream);
 /* same arithmetic on the host (used by the Python gen_M()/gen_A() wrappers for CPU tensors) */
 int ig_gen_tables_host(const float *te_h, int nb, int ne, float field, float *tab_h);
 
