@@ -46,6 +46,22 @@ def gen_tables(te, field):
     return tab
 
 
+def gen_tables_ahead(te, field, out):
+    """The table of the NEXT batch, launched in front of the objective that still uses the previous one (ig_gen_tables_ahead: it overlaps
+    the kernel before it in the stream and completes after it).  `te` must be complete already and `out`, a (nb, TAB_FLOATS) buffer, must
+    not be in use by that kernel: rotate three buffers (step i: gen_tables_ahead(te[i + 1], field, tabs[(i + 1) % 3]); objective(tabs[i % 3]))."""
+    te = _chk(te, "te")
+    if te.dim() == 3:
+        te = te[:, :, 0]
+    if not te.is_contiguous():
+        raise ValueError("gen_tables_ahead: te must be contiguous (a copy kernel in front of the table would defeat the look-ahead)")
+    nb, ne = te.shape
+    if tuple(out.shape) != (nb, L.TAB_FLOATS) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != te.device:
+        raise ValueError(f"gen_tables_ahead: out must be a contiguous float32 ({nb}, {L.TAB_FLOATS}) tensor on {te.device}")
+    L.check(L.load().ig_gen_tables_ahead(te.data_ptr(), nb, ne, float(field), out.data_ptr(), _stream()), "ig_gen_tables_ahead")
+    return out
+
+
 _scratch = {}
 
 

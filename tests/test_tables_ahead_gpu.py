@@ -28,6 +28,10 @@ def test_same_table_bit_for_bit(nb, ne):
     assert not torch.equal(a, b)
     L.check(lib.ig_gen_tables_ahead(te.data_ptr(), nb, ne, 1.5, b.data_ptr(), st), "ig_gen_tables_ahead")
     assert torch.equal(a, b)
+    c = torch.empty_like(b)
+    assert ops.gen_tables_ahead(te.unsqueeze(-1), 1.5, c) is c and torch.equal(a, c)     # the Python wrapper
+    with pytest.raises(ValueError):
+        ops.gen_tables_ahead(te, 1.5, c[:, :-1])
     assert lib.ig_gen_tables_ahead(0, nb, ne, 1.5, b.data_ptr(), st) == -1                  # IG_E_ARG
     assert lib.ig_gen_tables_ahead(te.data_ptr(), nb, 17, 1.5, b.data_ptr(), st) == -2     # IG_E_NE
 
