@@ -255,6 +255,21 @@ def event_times(fn, reps, warm=3, stream=None):
     return [a.elapsed_time(b) for a, b in evs]
 
 
+def back_to_back_ms(fn, reps, warm=3):
+    """SURVEY 8d's timing method: one event pair around `reps` back-to-back calls of fn() (ms per call).  Unlike an event pair per
+    call it keeps launch gaps and, for kernels launched with programmatic dependent launch, the prologue / tail overlap a loop has."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def dropin_leg(acqs, pm, te_dev, reps):
     """The step exactly as train-IDEAL-unsup.py:214-218,236,255 writes it, on the drop-in `wflib` with framework autograd --
     what an unmodified script reaches -- next to the one-line edit (`physics_loss_a2a`, the fused kernel behind autograd)."""
@@ -355,13 +370,21 @@ def configs_leg(device, peak, reps):
     tab3 = ops.gen_tables(te3d, FIELD)
     nvox3 = nb3 * h3 * h3
     up_rho = torch.randn((nb3, 2, h3, h3, 2), device=device)
-    t_f = float(np.median(event_times(lambda: ops.ideal_fwd(L.MODEL_WFPM, maps3, tab3, NE, R2_SC), reps)))
-    t_s = float(np.median(event_times(lambda: ops.get_rho_fwd(acqs3, pm3, tab3, R2_SC), reps)))
-    t_b = float(np.median(event_times(lambda: ops.get_rho_bwd(acqs3, pm3, tab3, up_rho, None, R2_SC), reps)))
+    def both(fn):
+        time.sleep(0.3)                                   # each leg starts from an idle board, not from the power cap the previous one left behind
+        t_pair = float(np.median(event_times(fn, reps)))
+        time.sleep(0.3)
+        return t_pair, float(back_to_back_ms(fn, 2 * reps))
+
+    t_f, t_f2 = both(lambda: ops.ideal_fwd(L.MODEL_WFPM, maps3, tab3, NE, R2_SC))
+    t_s, t_s2 = both(lambda: ops.get_rho_fwd(acqs3, pm3, tab3, R2_SC))
+    t_b, t_b2 = both(lambda: ops.get_rho_bwd(acqs3, pm3, tab3, up_rho, None, R2_SC))
     out["C3"] = {"what": "IDEAL_Layer(te per sample) forward, get_rho forward and adjoint, 256 x 192 x 192 x 6 (train-IDEAL-TEaug.py:217,304)",
                  "forward_ms": t_f, "forward_frac": frac(72, nvox3, t_f), "solve_ms": t_s, "solve_frac": frac(72, nvox3, t_s),
                  "solve_bwd_ms": t_b, "solve_bwd_frac": frac(128, nvox3, t_b),
-                 "voxel_echoes_per_s": nvox3 * NE / ((t_f + t_s + t_b) * 1e-3)}
+                 "voxel_echoes_per_s": nvox3 * NE / ((t_f + t_s + t_b) * 1e-3),
+                 "back_to_back": {"forward_ms": t_f2, "solve_ms": t_s2, "solve_bwd_ms": t_b2, "voxel_echoes_per_s": nvox3 * NE / ((t_f2 + t_s2 + t_b2) * 1e-3)},
+                 "timing": "*_ms: median of one event pair per launch; back_to_back: one event pair around 2 x reps launches (SURVEY 8d)"}
     del acqs3, pm3, maps3, up_rho
 
     # ---- the published model's own objectives on the C2 batch (train-IDEAL-unsup.py:214-231 UQ stage, :267-292 R2* stage) -------------
@@ -372,13 +395,14 @@ def configs_leg(device, peak, reps):
     pv = torch.rand((NB, 1, H, W, 1), device=device, generator=g) * 4e-3
     rv = torch.rand((NB, 1, H, W, 1), device=device, generator=g) * 3e-3
     rm = pm2[..., 1:2].contiguous()
-    t_uq = float(np.median(event_times(lambda: ops.a2a_uq_loss(acqs2, pm2, pv, rm, rv, tab2), reps)))
-    t_ri = float(np.median(event_times(lambda: ops.a2a_rician_loss(acqs2, pm2, pv, rm, rv, tab2), reps)))
+    t_uq, t_uq2 = both(lambda: ops.a2a_uq_loss(acqs2, pm2, pv, rm, rv, tab2))
+    t_ri, t_ri2 = both(lambda: ops.a2a_rician_loss(acqs2, pm2, pv, rm, rv, tab2))
     out["C2_uncertainty_objectives"] = {
         "what": "acq_to_acq + acq_uncertainty(stop_gradient) + VarMeanSquaredError (ig_a2a_uq_loss) and its Rician R2*-stage twin (ig_a2a_rician_loss): "
                 "loss + all gradients in one kernel each, 64 x 384 x 384 x 6, 88 algorithmic bytes per voxel",
         "uq_ms": t_uq, "uq_frac": frac(88, NB * H * W, t_uq), "uq_voxel_echoes_per_s": NB * H * W * NE / (t_uq * 1e-3),
         "rician_ms": t_ri, "rician_frac": frac(88, NB * H * W, t_ri), "rician_voxel_echoes_per_s": NB * H * W * NE / (t_ri * 1e-3),
+        "back_to_back": {"uq_ms": t_uq2, "uq_frac": frac(88, NB * H * W, t_uq2), "rician_ms": t_ri2, "rician_frac": frac(88, NB * H * W, t_ri2)},
         "note": "both are bound by instruction issue, not by HBM (DESIGN.md 4.2, profiles/ncu_kernels_r02.md)"}
     del acqs2, pm2, pv, rv, rm
 
@@ -401,7 +425,7 @@ def configs_leg(device, peak, reps):
         return (m * 0.97).contiguous(), acq, ted, tab
 
     m64, a64, _, tab64 = c4_batch(NB)
-    t64 = float(np.median(event_times(lambda: ops.ideal_loss(L.MODEL_MAGPHA, m64, a64, tab64, R2_SC), reps)))
+    t64, t64b = both(lambda: ops.ideal_loss(L.MODEL_MAGPHA, m64, a64, tab64, R2_SC))
     del m64, a64
     m3, a3, te3s, tab3s = c4_batch(3)
     g3, l3 = torch.empty_like(m3), torch.empty(1, device=device)
@@ -417,6 +441,7 @@ def configs_leg(device, peak, reps):
     us3 = graph_us(c4_abi)
     out["C4"] = {"what": "IDEAL_mag_Layer(sep_phase) forward + mask + MSE + backward fused (ig_ideal_loss[magpha], bipolar), 384 x 384 x 6",
                  "nb3_us": us3, "nb3_voxel_echoes_per_s": 3 * H * W * NE / (us3 * 1e-6), "nb64_ms": t64, "nb64_frac": frac(112, NB * H * W, t64),
+                 "nb64_ms_back_to_back": t64b, "nb64_frac_back_to_back": frac(112, NB * H * W, t64b),
                  "nb64_voxel_echoes_per_s": NB * H * W * NE / (t64 * 1e-3),
                  "note": "nb3: the script's own batch, ig_gen_tables + ig_ideal_loss replayed from a CUDA graph; nb64: roofline batch"}
     return out
