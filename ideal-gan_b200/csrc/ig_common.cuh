@@ -71,11 +71,21 @@ __device__ __forceinline__ float vadd(float a, float b) { return a + b; }
 __device__ __forceinline__ float vsub(float a, float b) { return a - b; }
 __device__ __forceinline__ float vneg(float a) { return -a; }
 
+#ifdef IG_NO_F32X2
+// experiment build (make SUFFIX=_s EXTRA=-DIG_NO_F32X2=1): the two lanes as scalar FFMA / FMUL / FADD.  An FFMA2 holds the issue port and the
+// FMA pipe for two cycles (tools/ubench_f32x2.cu), so packing buys no arithmetic rate; this build measures what it costs or saves otherwise.
+__device__ __forceinline__ pk vfma(pk a, pk b, pk c) { return mk(fmaf(a.d.x, b.d.x, c.d.x), fmaf(a.d.y, b.d.y, c.d.y)); }
+__device__ __forceinline__ pk vmul(pk a, pk b) { return mk(a.d.x * b.d.x, a.d.y * b.d.y); }
+__device__ __forceinline__ pk vadd(pk a, pk b) { return mk(a.d.x + b.d.x, a.d.y + b.d.y); }
+__device__ __forceinline__ pk vneg(pk a) { return mk(-a.d.x, -a.d.y); }
+__device__ __forceinline__ pk vsub(pk a, pk b) { return mk(a.d.x - b.d.x, a.d.y - b.d.y); }
+#else
 __device__ __forceinline__ pk vfma(pk a, pk b, pk c) { pk r; r.d = __ffma2_rn(a.d, b.d, c.d); return r; }
 __device__ __forceinline__ pk vmul(pk a, pk b) { pk r; r.d = __fmul2_rn(a.d, b.d); return r; }
 __device__ __forceinline__ pk vadd(pk a, pk b) { pk r; r.d = __fadd2_rn(a.d, b.d); return r; }
 __device__ __forceinline__ pk vneg(pk a) { return mk(-a.d.x, -a.d.y); }
 __device__ __forceinline__ pk vsub(pk a, pk b) { return vfma(mk(-1.0f, -1.0f), b, a); }
+#endif
 // scalar (block-uniform table coefficient) x packed: the compiler folds make_float2(s, s) into FFMA2's
 // scalar-broadcast operand form (R.F32), so no register pair is materialised.
 __device__ __forceinline__ pk vfma(float a, pk b, pk c) { return vfma(mk(a, a), b, c); }
