@@ -471,6 +471,8 @@ int magpha_loss_ring(const float *maps, const float *acqs, const float *tab, int
                      float *loss, void *scratch, cudaStream_t st);
 int row_loss_ring(int model, const float *maps, int rows, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float inv_n,
                   float *gmaps, float *shat, float *loss, void *scratch, cudaStream_t st);
+int row_bwd_ring(int model, const float *maps, int rows, const float *gout, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float *gmaps,
+                 cudaStream_t st);
 int pdff_unc_ring(const float *acqs, const float *phi_mean, const float *phi_var, const float *r2_mean, const float *r2_var, const float *tab, int nb,
                   int ne, int nv, float r2_sc, float *rho, float *cov, cudaStream_t st);
 int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, const float *phi_var, const float *r2_mean, const float *r2_var,

@@ -270,11 +270,17 @@ template <int MODEL, int MODE> static int launch_ideal(const FwdParams &p, cudaS
     }
     return dispatch_ne(p.ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
+        if constexpr (MODE == MODE_BWD && MODEL != IG_MODEL_MAGPHA) {
+            if (packed && p.ne > 8) {      // 9..12 echoes, 128-voxel rows: the adjoint on the TMA ring (ig_ring_ops.cu, RowLossOp<.., BWD>)
+                const int rc = row_bwd_ring(MODEL, p.maps, p.rows_or_ch, p.gout, p.tab, p.nb, p.ne, p.nv, p.r2_sc, p.flags, p.gmaps, st);
+                if (rc != IG_E_UNSUPPORTED) return rc;
+            }
+        }
         if constexpr (MODE == MODE_LOSS) {
             // measured at 64 x 384 x 384 x 6: the grid + finish pair wins for the complex-row models (0.159 vs 0.165 ms), the
             // persistent kernel for mag/phase, whose 128 registers leave too few warps for the one-tile-per-block shape (0.213 vs 0.251 ms)
             if (MODEL != IG_MODEL_MAGPHA) {
-                if (packed) {      // 128-voxel rows, <= 8 echoes, <= 4 map rows: the TMA ring (ig_ring_ops.cu, RowLossOp)
+                if (packed) {      // 128-voxel rows, <= 12 echoes, <= 4 map rows: the TMA ring (ig_ring_ops.cu, RowLossOp)
                     const int rc = row_loss_ring(MODEL, p.maps, p.rows_or_ch, p.acqs, p.tab, p.nb, p.ne, p.nv, p.r2_sc, p.flags, p.inv_n, p.gmaps, p.out, p.loss,
                                                  p.scratch, st);
                     if (rc != IG_E_UNSUPPORTED) return rc;

@@ -22,6 +22,19 @@ __device__ __forceinline__ cx<pk> conj_rot(pk cw, pk sw, const float4 &r) {
 }
 __device__ __forceinline__ bool all_zero(const float4 &r) { return r.x == 0.f && r.y == 0.f && r.z == 0.f && r.w == 0.f; }
 
+// One instantiation per echo count instead of a bucket with a run-time count: behind `if (e < ne)` the compiler cannot lift the stage reads of
+// the later echoes over the earlier echoes' math, and with 8-16 consumer warps per SM that latency shows (measured, 64 x 384 x 384: the
+// acq_to_acq adjoint at 7 echoes in the 8-echo bucket 0.226 ms against 0.201 ms AT 8 echoes; the WF-PM adjoint at 9 in the 12-echo bucket
+// 0.238 against 0.205 ms at 12).
+template <int N, int HI, typename F> static int dispatch_exact_ne(int ne, F &&f) {
+    if constexpr (N > HI) {
+        return IG_E_UNSUPPORTED;
+    } else {
+        if (ne == N) return f(std::integral_constant<int, N>{});
+        return dispatch_exact_ne<N + 1, HI>(ne, f);
+    }
+}
+
 // =================================================================================================
 // acq_to_acq adjoint (math: ig_solve.cu, a2a_bwd_kernel)
 // =================================================================================================
@@ -142,15 +155,11 @@ int a2a_bwd_ring(const float *acqs, const float *pm, long pm_bstride, const floa
     A2aBwdParams p{};
     p.acqs = acqs; p.pm = pm; p.pm_bstride = pm_bstride; p.tab = tab; p.g_rho = g_rho; p.g_shat = g_shat; p.g_acqs = g_acqs; p.g_pm = g_pm;
     p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
-    auto go = [&](auto ne_c) {
+    // 2..8 echoes: two blocks per SM; 9..12 (train-IDEAL-TEaug.py:614-618): 76-100 KB stages, one block per SM, two stages
+    return dispatch_exact_ne<2, 12>(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        if (ne == NE) return g_acqs ? launch_bwd<A2aBwdOp<NE, true, true>>(p, st) : launch_bwd<A2aBwdOp<NE, true, false>>(p, st);
-        return g_acqs ? launch_bwd<A2aBwdOp<NE, false, true>>(p, st) : launch_bwd<A2aBwdOp<NE, false, false>>(p, st);
-    };
-    if (ne <= 4) return go(std::integral_constant<int, 4>{});
-    if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    if (ne <= 8) return go(std::integral_constant<int, 8>{});
-    return go(std::integral_constant<int, 12>{});      // 9..12 echoes (train-IDEAL-TEaug.py:614-618): 100 KB stages, one block per SM, two stages
+        return g_acqs ? launch_bwd<A2aBwdOp<NE, true, true>>(p, st) : launch_bwd<A2aBwdOp<NE, true, false>>(p, st);
+    });
 }
 
 // =================================================================================================
@@ -184,6 +193,7 @@ template <int NE, bool EXACT> struct MagphaLossOp {
         const size_t map_elems = static_cast<size_t>(2) * nv * 4;
         float *g_b = p.gmaps + b * map_elems;
         // background chunk (every measured component zero): the mask removes every residual -> loss 0, gradient 0
+        // (BWD: a chunk whose upstream is zero everywhere has a zero gradient as well)
         bool nz = false;
         if (active) {
 #pragma unroll
@@ -280,15 +290,21 @@ struct RowLossParams {
     float r2_sc, inv_n;
 };
 
-template <int MODEL, int NE, bool EXACT> struct RowLossOp {
+// BWD: the adjoint alone (IDEAL_Layer's autodiff, train-IDEAL-TEaug.py:192 with up to 12 echoes): `acqs` carries the upstream gradient, which
+// takes the place of the masked residual; no loss, no work counter (tiles are dealt round-robin), gradients unscaled.
+template <int MODEL, int NE, bool EXACT, bool BWD = false> struct RowLossOp {
     using Params = RowLossParams;
     struct Shared {};
     static constexpr int kNE = NE, kMaps = 2;
-    static constexpr bool kExact = EXACT, kDynamic = true, kLoss = true, kWritesStage = false;
+    static constexpr bool kExact = EXACT, kDynamic = !BWD, kLoss = !BWD, kWritesStage = false;
     static constexpr int fpv(int) { return 2; }
     static constexpr int planes_max(int m) { return m == 0 ? 4 : NE; }
     static constexpr int kStageBytes = (4 + NE) * kRingTileVox * 8 + ((NE * 64 + 127) / 128) * 128;
-    static constexpr int kStages = 2 * 3 * kStageBytes <= kRingSmemBudget ? 3 : 2, kMinBlocks = 2;
+    // two blocks per SM where two stages each fit (<= 8 echoes), one block with three 65 KB stages for 9..12 echoes (as A2aBwdOp)
+    static constexpr bool kTwoBlocks = 2 * 2 * kStageBytes <= kRingSmemBudget;
+    static constexpr int kStages = kTwoBlocks ? (2 * 3 * kStageBytes <= kRingSmemBudget ? 3 : 2) : (3 * kStageBytes <= kRingSmemBudget ? 3 : 2);
+    static constexpr int kMinBlocks = kTwoBlocks ? 2 : 1;
+    static_assert(kStages * kStageBytes <= kRingSmemBudget, "the ring needs at least two stages in shared memory");
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? p.rows : ne; }
     __device__ static void prologue(Shared &) {}
 
@@ -301,6 +317,7 @@ template <int MODEL, int NE, bool EXACT> struct RowLossOp {
         float *g_b = p.gmaps + static_cast<size_t>(b) * rows * nv * 2;
         const pk zero = splat<pk>(0.f);
         // background chunk (every measured component zero): the mask removes every residual -> loss 0, gradient 0
+        // (BWD: a chunk whose upstream is zero everywhere has a zero gradient as well)
         bool nz = false;
         if (active) {
 #pragma unroll
@@ -350,10 +367,15 @@ template <int MODEL, int NE, bool EXACT> struct RowLossOp {
                 const cx<pk> yhat = caffine(x.rhoW, R.c_re, R.c_im, x.rhoF);
                 const cx<pk> shat = cmulv(w, yhat);
                 const float4 A = sA[e * kPlaneF4];
-                const cx<pk> G{mask_sub(shat.re, mk(A.x, A.z)), mask_sub(shat.im, mk(A.y, A.w))};
-                lsum = vfma(G.re, G.re, lsum);
-                lsum = vfma(G.im, G.im, lsum);
-                if (p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                cx<pk> G;
+                if constexpr (BWD) {
+                    G = cx<pk>{mk(A.x, A.z), mk(A.y, A.w)};
+                } else {
+                    G = cx<pk>{mask_sub(shat.re, mk(A.x, A.z)), mask_sub(shat.im, mk(A.y, A.w))};
+                    lsum = vfma(G.re, G.re, lsum);
+                    lsum = vfma(G.im, G.im, lsum);
+                    if (p.shat) st_cx(p.shat + acq_b + static_cast<size_t>(e) * nv * 2, v0, shat);
+                }
                 const cx<pk> g = cmulc(w, G);
                 a.sg.re = vadd(a.sg.re, g.re);
                 a.sg.im = vadd(a.sg.im, g.im);
@@ -365,29 +387,41 @@ template <int MODEL, int NE, bool EXACT> struct RowLossOp {
                 else a.bq = vfma(R.sgn, q.im, a.bq);
             }
         }
-        loss_part += hsum(lsum);
-        write_grads<pk, MODEL>(g_b, rows, nv, v0, p.flags, x, a, p.r2_sc, 2.0f * p.inv_n);
+        if constexpr (!BWD) loss_part += hsum(lsum);
+        write_grads<pk, MODEL>(g_b, rows, nv, v0, p.flags, x, a, p.r2_sc, BWD ? 1.0f : 2.0f * p.inv_n);
     }
 };
 
-int row_loss_ring(int model, const float *maps, int rows, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float inv_n,
-                  float *gmaps, float *shat, float *loss, void *scratch, cudaStream_t st) {
-    if (ne > 8 || rows > 4 || nv % 128 != 0 || !aligned16(gmaps) || (shat && !aligned16(shat)) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24))
+template <bool BWD>
+static int row_ring(int model, const float *maps, int rows, const float *acqs_or_gout, const float *tab, int nb, int ne, int nv, float r2_sc, int flags,
+                    float inv_n, float *gmaps, float *shat, float *loss, void *scratch, cudaStream_t st) {
+    if (ne > 12 || rows > 4 || nv % 128 != 0 || !aligned16(gmaps) || (shat && !aligned16(shat)) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24))
         return IG_E_UNSUPPORTED;
     RowLossParams p{};
-    p.maps = maps; p.acqs = acqs; p.tab = tab; p.gmaps = gmaps; p.shat = shat; p.loss = loss; p.scratch = scratch;
+    p.maps = maps; p.acqs = acqs_or_gout; p.tab = tab; p.gmaps = gmaps; p.shat = shat; p.loss = loss; p.scratch = scratch;
     p.nb = nb; p.ne = ne; p.nv = nv; p.rows = rows; p.flags = flags; p.r2_sc = r2_sc; p.inv_n = inv_n;
     RingMaps m{};
     if (!ring_tensor_map(&m.m[0], maps, nv, 2, static_cast<long>(nb) * rows, static_cast<long>(nv) * 2, rows)) return IG_E_UNSUPPORTED;
-    if (!ring_tensor_map(&m.m[1], acqs, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
-    auto go = [&](auto ne_c) {
+    if (!ring_tensor_map(&m.m[1], acqs_or_gout, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
+    // 1..8 echoes: two blocks per SM; 9..12: one block per SM, three 53-65 KB stages.  The adjoint alone runs here beyond 8 echoes only.
+    return dispatch_exact_ne<(BWD ? 9 : 1), 12>(ne, [&](auto ne_c) {
         constexpr int NE = decltype(ne_c)::value;
-        if (model == IG_MODEL_WFPM) return ne == NE ? ring_launch<RowLossOp<IG_MODEL_WFPM, NE, true>>(p, m, st) : ring_launch<RowLossOp<IG_MODEL_WFPM, NE, false>>(p, m, st);
-        return ne == NE ? ring_launch<RowLossOp<IG_MODEL_FFPD, NE, true>>(p, m, st) : ring_launch<RowLossOp<IG_MODEL_FFPD, NE, false>>(p, m, st);
-    };
-    if (ne <= 4) return go(std::integral_constant<int, 4>{});
-    if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    return go(std::integral_constant<int, 8>{});
+        if (model == IG_MODEL_WFPM) return ring_launch<RowLossOp<IG_MODEL_WFPM, NE, true, BWD>>(p, m, st);
+        return ring_launch<RowLossOp<IG_MODEL_FFPD, NE, true, BWD>>(p, m, st);
+    });
+}
+
+int row_loss_ring(int model, const float *maps, int rows, const float *acqs, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float inv_n,
+                  float *gmaps, float *shat, float *loss, void *scratch, cudaStream_t st) {
+    return row_ring<false>(model, maps, rows, acqs, tab, nb, ne, nv, r2_sc, flags, inv_n, gmaps, shat, loss, scratch, st);
+}
+
+// the adjoint of the complex-row forward models for 9..12 echoes (the plain kernel holds 12 upstream echoes of two voxels in 110-126 registers
+// and reaches 80-84 % of the HBM rate there; below 9 echoes it is at 95-99 % and stays the path)
+int row_bwd_ring(int model, const float *maps, int rows, const float *gout, const float *tab, int nb, int ne, int nv, float r2_sc, int flags, float *gmaps,
+                 cudaStream_t st) {
+    if (ne <= 8 || !aligned16(gout)) return IG_E_UNSUPPORTED;
+    return row_ring<true>(model, maps, rows, gout, tab, nb, ne, nv, r2_sc, flags, 1.0f, gmaps, nullptr, nullptr, nullptr, st);
 }
 
 // =================================================================================================

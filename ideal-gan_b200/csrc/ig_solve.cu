@@ -1320,7 +1320,9 @@ extern "C" int ig_get_rho_bwd(const float *acqs_d, const float *pm_d, long pm_bs
     p.acqs = acqs_d; p.pm = pm_d; p.pm_bstride = pm_bstride; p.bip = bip_d; p.bip_bstride = bip_bstride; p.tab = tab_d;
     p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.flags = flags; p.g_rho = g_rho_d; p.g_demod = g_demod_d;
     p.g_acqs = g_acqs_d; p.g_pm = g_pm_d; p.g_bip = g_bip_d;
-    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 &&
+    // beyond 8 echoes two voxels per thread need 94-106 registers (16 warps per SM): one voxel per thread (57 registers, 32 warps) measured
+    // 0.301 against 0.332 ms at 9 echoes and 0.361 against 0.388 ms at 12 (64 x 384 x 384, dPM + dS; profiles/history_r02.md section 11)
+    const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && bip_bstride % 4 == 0 && (ne <= 8 || flat) &&
                         all_aligned({acqs_d, pm_d, bip_d, g_rho_d, g_demod_d, g_acqs_d, g_pm_d, g_bip_d});
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_ne(ne, [&](auto ne_c) {

@@ -135,16 +135,23 @@ def test_pdff_uncertainty_ring_vs_plain_kernel_and_fp64_oracle(shape, rem):
     assert_close(cov.cpu().numpy(), cov_p.cpu().numpy(), 2 * tol_cov, "cov ring vs plain")
 
 
-@pytest.mark.parametrize("shape", [(3, 16, 16, 6), (2, 40, 48, 5), (1, 384, 384, 6), (2, 64, 96, 8), (2, 64, 64, 3)])
+def _te(nb, ne, rng):
+    # train-IDEAL-TEaug.py:624-626: the bipolar runs draw 6..12 echoes 0.9-1.2 ms apart
+    return synth.te_random(nb, ne, rng, d_te_min=0.9e-3, d_te_d=0.3e-3) if ne > 8 else synth.te_random(nb, ne, rng)
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 16, 6), (2, 40, 48, 5), (1, 384, 384, 6), (2, 64, 96, 8), (2, 64, 64, 3), (2, 40, 48, 9), (1, 192, 192, 12),
+                                   (3, 32, 32, 11)])
 @pytest.mark.parametrize("model,rows", [(L.MODEL_WFPM, 3), (L.MODEL_WFPM, 4), (L.MODEL_FFPD, 3)], ids=["wfpm", "wfpm-bipolar", "ffpd"])
 def test_forward_objective_of_the_complex_row_models_ring_vs_plain_kernel(shape, model, rows):
-    """ig_ideal_loss for WF-PM (3 rows, 4 rows with the bipolar one) and ff/pd/phase maps on the generic ring (128-voxel rows, <= 8
-    echoes) against the plain kernels (forced by measurements that start 8 bytes into an allocation), loss, gradient and S_hat."""
+    """ig_ideal_loss for WF-PM (3 rows, 4 rows with the bipolar one) and ff/pd/phase maps on the generic ring (128-voxel rows, <= 12
+    echoes; 9..12 on one block per SM) against the plain kernels (forced by measurements that start 8 bytes into an allocation), loss,
+    gradient and S_hat."""
     nb, H, W, ne = shape
     rng = np.random.default_rng(5 + nb + ne + rows)
     maps_np = synth.ffpd_maps(nb, H, W, rng) if model == L.MODEL_FFPD else synth.wfpm_maps(nb, H, W, rng, bipolar=(rows == 4))
     maps = torch.from_numpy(maps_np).cuda()
-    te = torch.from_numpy(synth.te_random(nb, ne, rng)).cuda()
+    te = torch.from_numpy(_te(nb, ne, rng)).cuda()
     tab = ops.gen_tables(te, 1.5)
     sig = ops.ideal_fwd(model, maps, tab, ne)
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -163,3 +170,33 @@ def test_forward_objective_of_the_complex_row_models_ring_vs_plain_kernel(shape,
     loss2, gmaps2, _ = ops.ideal_loss(model, est, acqs, tab)              # without S_hat: background chunks take the zero-fill shortcut
     assert abs(loss2.item() - loss_p.item()) <= 2e-6 * abs(loss_p.item())
     assert_close(gmaps2.cpu().numpy(), gmaps_p.cpu().numpy(), 5e-6, "gradient (no S_hat) ring vs plain")
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 48, 9), (1, 192, 192, 12), (3, 32, 32, 11), (2, 64, 64, 10), (1, 384, 384, 12)])
+@pytest.mark.parametrize("model,rows", [(L.MODEL_WFPM, 3), (L.MODEL_WFPM, 4), (L.MODEL_FFPD, 3)], ids=["wfpm", "wfpm-bipolar", "ffpd"])
+def test_adjoint_of_the_complex_row_models_ring_vs_plain_kernel_and_oracle(shape, model, rows):
+    """ig_ideal_bwd beyond 8 echoes (IDEAL_Layer's autodiff in the bipolar train-IDEAL-TEaug.py runs, 6..12 echoes) goes through the generic
+    ring; an upstream gradient that starts 8 bytes into an allocation forces the plain kernel.  Both against each other, and the ring
+    against the oracle's autograd of IDEAL_model / IDEAL_mag."""
+    from oracle import ideal_oracle as orc
+    nb, H, W, ne = shape
+    rng = np.random.default_rng(17 + nb + ne + rows)
+    maps_np = synth.ffpd_maps(nb, H, W, rng) if model == L.MODEL_FFPD else synth.wfpm_maps(nb, H, W, rng, bipolar=(rows == 4))
+    te_np = _te(nb, ne, rng)
+    maps = torch.from_numpy(maps_np).cuda()
+    tab = ops.gen_tables(torch.from_numpy(te_np).cuda(), 1.5)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    gout = torch.randn((nb, ne, H, W, 2), device="cuda", generator=g)
+    gout[:, :, : H // 4] = 0.0                                           # whole chunks without upstream: the zero-fill shortcut
+    gmaps = ops.ideal_bwd(model, maps, tab, ne, gout)
+    buf = torch.empty(gout.numel() + 2, device="cuda")
+    g_off = buf[2:].view_as(gout)
+    g_off.copy_(gout)
+    assert g_off.data_ptr() % 16 == 8
+    gmaps_p = ops.ideal_bwd(model, maps, tab, ne, g_off)
+    assert_close(gmaps.cpu().numpy(), gmaps_p.cpu().numpy(), 5e-6, "adjoint ring vs plain")
+    if H * W <= 64 * 64:
+        m = torch.from_numpy(maps_np).requires_grad_(True)
+        sig = (orc.IDEAL_mag if model == L.MODEL_FFPD else orc.IDEAL_model)(m, [1.5, torch.from_numpy(te_np)])
+        (ref,) = torch.autograd.grad(sig, [m], grad_outputs=gout.cpu())
+        assert_close(gmaps.cpu().numpy(), ref.numpy(), 1e-5, "adjoint (ring) vs oracle autograd")

@@ -78,6 +78,16 @@ def main():
 
         if "loss" in which:
             rec("a2a_loss", 8 * ne + 16, lambda: ops.a2a_loss(acqs, pm, tab))
+        if "plain" in which:
+            # the operators an unmodified train-IDEAL-TEaug.py step reaches (IDEAL_Layer, get_rho and their adjoints, 2..12 echoes) and acq_to_acq forward
+            up_r = torch.randn((nb, 2, H, W, 2), device=dev, generator=g)
+            rec("ideal_fwd", 8 * ne + 24, lambda: ops.ideal_fwd(L.MODEL_WFPM, maps, tab, ne))
+            rec("ideal_bwd", 8 * ne + 48, lambda: ops.ideal_bwd(L.MODEL_WFPM, maps, tab, ne, acqs))
+            rec("ideal_loss_wfpm", 8 * ne + 48, lambda: ops.ideal_loss(L.MODEL_WFPM, maps, acqs, tab))
+            rec("get_rho_fwd", 8 * ne + 24, lambda: ops.get_rho_fwd(acqs, pm, tab))
+            rec("get_rho_bwd", 16 * ne + 32, lambda: ops.get_rho_bwd(acqs, pm, tab, up_r, None))
+            rec("a2a_fwd", 16 * ne + 24, lambda: ops.a2a_fwd(acqs, pm, tab))
+            del up_r
         if "bwd" in which or "bwd_ds" in which:
             up = torch.randn(acqs.shape, device=dev, generator=g)
             if "bwd" in which:
