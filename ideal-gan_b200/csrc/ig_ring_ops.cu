@@ -55,9 +55,12 @@ template <int NE, bool EXACT, bool DS> struct A2aBwdOp {
     static constexpr int fpv(int) { return 2; }
     static constexpr int planes_max(int m) { return m < 2 ? NE : 1; }
     static constexpr int kStageBytes = (2 * NE + 1) * kRingTileVox * 8 + ((NE * 64 + 127) / 128) * 128;
-    static constexpr bool kTwoBlocks = 2 * 2 * kStageBytes <= kRingSmemBudget;
-    // two blocks per SM with three (or two) stages each where they fit; one block with as many stages as fit otherwise (ne = 9..12: two)
-    static constexpr int kStages = kTwoBlocks ? (2 * 3 * kStageBytes > kRingSmemBudget ? 2 : 3) : (3 * kStageBytes <= kRingSmemBudget ? 3 : 2);
+    // dPM only: two blocks per SM with three (or two) stages each where they fit, one block with as many stages as fit otherwise (9..12 echoes:
+    // two).  With dS as well (ne more output planes per voxel) one block per SM with up to four stages is as fast or faster at every echo
+    // count (same-call A/B at 4 / 6 / 8 echoes: 0.1765 -> 0.1642, 0.2626 -> 0.2604, 0.3291 -> 0.3283 ms).
+    static constexpr bool kTwoBlocks = !DS && 2 * 2 * kStageBytes <= kRingSmemBudget;
+    static constexpr int kOneBlockStages = 4 * kStageBytes <= kRingSmemBudget ? 4 : (3 * kStageBytes <= kRingSmemBudget ? 3 : 2);
+    static constexpr int kStages = kTwoBlocks ? (2 * 3 * kStageBytes > kRingSmemBudget ? 2 : 3) : kOneBlockStages;
     static constexpr int kMinBlocks = kTwoBlocks ? 2 : 1;
     static_assert(kStages * kStageBytes <= kRingSmemBudget, "the ring needs at least two stages in shared memory");
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : (m == 1 ? (p.g_shat ? ne : 0) : 1); }
