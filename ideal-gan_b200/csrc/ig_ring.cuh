@@ -14,12 +14,21 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "ig_common.cuh"
 
 namespace ig {
 
 constexpr int kRingTileVox = 512, kRingChunkVox = 64, kRingChunks = kRingTileVox / kRingChunkVox;
-constexpr int kRingConsumerWarps = 8, kRingThreads = kRingConsumerWarps * 32 + 32;
+// Consumer warps per block: 8 unless the Op names its own count (`kConsumerWarps`).  8 + the producer = 9 warps per block, 18 per SM at two
+// blocks: the fuller scheduler holds 5 warps, so a thread gets 96 registers.  7 + 1 = 8 warps per block is 4 per scheduler and 128 registers:
+// the issue-bound objectives whose 96-register builds spill (Rician, UQ) run 4-6 % faster on seven warps, the HBM-bound operators and the C2
+// objective (no spills at 95 registers) do not (profiles/history_r02.md section 12).
+constexpr int kRingConsumerWarps = 8;
+template <class Op, class = void> struct RingCw { static constexpr int value = kRingConsumerWarps; };
+template <class Op> struct RingCw<Op, std::void_t<decltype(Op::kConsumerWarps)>> { static constexpr int value = Op::kConsumerWarps; };
+template <class Op> constexpr int ring_threads() { return RingCw<Op>::value * 32 + 32; }
 constexpr int kRingMaxMaps = 5;
 
 struct RingMaps {
@@ -45,7 +54,7 @@ __host__ __device__ constexpr int ring_inner_floats(int fpv) { return 128 * fpv 
 __host__ __device__ constexpr int ring_tile_rows(int fpv) { return kRingTileVox * fpv / ring_inner_floats(fpv); }
 
 template <class Op>
-__global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(const typename Op::Params p, const __grid_constant__ RingMaps maps) {
+__global__ void __launch_bounds__(ring_threads<Op>(), Op::kMinBlocks) ring_kernel(const typename Op::Params p, const __grid_constant__ RingMaps maps) {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     using Lay = RingLayout<Op>;
     constexpr int STAGES = Op::kStages, NE = Op::kNE;
@@ -68,7 +77,8 @@ __global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(cons
     grid_dependency_wait();          // PDL: everything above overlaps the tail of the previous kernel in the stream (ig_gen_tables)
     __syncthreads();
     float loss_part = 0.f;
-    if (threadIdx.x >= kRingConsumerWarps * 32) {
+    constexpr int kCw = RingCw<Op>::value;
+    if (threadIdx.x >= kCw * 32) {
         // ---------------- producer warp: lane 0 owns the work counter, the barriers and the copies ----------------
         const int lane = threadIdx.x & 31;
         unsigned *next_tile = reinterpret_cast<unsigned *>(p.scratch) + 1;
@@ -84,6 +94,7 @@ __global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(cons
 #pragma unroll
         for (int m = 0; m < Op::kMaps; ++m) tx += static_cast<uint32_t>(Op::planes(m, ne, p)) * Lay::plane_bytes(m);
         bool released = false;
+        int ends_left = (kCw + kRingChunks - 1) / kRingChunks;      // every consumer warp draws one chunk past the data: enough marker stages for all of them
         for (int it = 0;; ++it) {
             const int s = it % STAGES;
             int k;
@@ -105,7 +116,10 @@ __global__ void __launch_bounds__(kRingThreads, Op::kMinBlocks) ring_kernel(cons
                 else mbar_expect_tx(&full_bar[s], tx);
             }
             __syncwarp();
-            if (end) break;                                  // one marker stage: each of the 8 consumer warps draws one chunk of it
+            if (end) {
+                if (--ends_left == 0) break;
+                continue;
+            }
             if (lane == 0) {
                 unsigned char *stage = stage_mem + s * Lay::stage_bytes;
 #pragma unroll
@@ -186,13 +200,13 @@ template <class Op> int ring_launch(typename Op::Params p, const RingMaps &maps,
     IG_CUDA(cudaGetDevice(&dev));
     IG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     IG_CUDA(cudaFuncSetAttribute(ring_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::smem_bytes));
-    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<Op>, kRingThreads, Lay::smem_bytes));
+    IG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<Op>, ring_threads<Op>(), Lay::smem_bytes));
     const long tiles = static_cast<long>(p.nb) * tiles_ps;
     long g = static_cast<long>(sms) * (occ > 0 ? occ : 1);
     if (g > tiles) g = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(g));
-    cfg.blockDim = dim3(kRingThreads);
+    cfg.blockDim = dim3(ring_threads<Op>());
     cfg.dynamicSmemBytes = static_cast<size_t>(Lay::smem_bytes);
     cfg.stream = st;
     cudaLaunchAttribute attr{};

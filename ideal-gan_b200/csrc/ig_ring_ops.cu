@@ -451,7 +451,10 @@ template <int NE, bool EXACT> struct RicianOp {
     static constexpr int planes_max(int m) { return m == 0 ? NE : 1; }
     static constexpr int kStageBytes = (NE + 1) * kRingTileVox * 8 + 3 * kRingTileVox * 4 + ((NE * 64 + 127) / 128) * 128;
     static constexpr int kStatic = kBesselRows * 48 + 256;
-    static constexpr int kStages = 2 * (3 * kStageBytes + kStatic) <= kRingSmemBudget ? 3 : 2, kMinBlocks = 2;
+    // One block of 15 consumer warps + the producer per SM (16 warps = 4 per scheduler = 128 registers per thread, no spills) on one ring of
+    // six stages.  Same-call A/B at 64 x 384 x 384 x 6, masked / unmasked: two blocks of 8 + 1 warps at 96 registers (88 B of spills)
+    // 0.2728 / 0.3200 ms, two blocks of 7 + 1 at 128 registers 0.2605 / 0.3014, this 0.2452 / 0.2933.
+    static constexpr int kStages = 6 * kStageBytes + kStatic <= kRingSmemBudget ? 6 : 4, kMinBlocks = 1, kConsumerWarps = 15;
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : ((m >= 3 && !p.r2_mean) ? 0 : 1); }
     __device__ static void prologue(Shared &sh) { stage_bessel_table(sh.btab); }
 
@@ -610,7 +613,9 @@ template <int NE, bool EXACT> struct PdffUncOp {
     static constexpr int fpv(int m) { return m == 0 ? 2 : 1; }
     static constexpr int planes_max(int m) { return m == 0 ? NE : 1; }
     static constexpr int kStageBytes = NE * kRingTileVox * 8 + 4 * kRingTileVox * 4 + ((NE * 64 + 127) / 128) * 128;
-    static constexpr int kStages = 2 * 3 * kStageBytes <= kRingSmemBudget ? 3 : 2, kMinBlocks = 2;
+    // one block of 15 consumer warps + the producer per SM at 128 registers, one ring of six (four) stages: same-call A/B against two blocks of
+    // 8 + 1 warps at 96 registers 0.1842 -> 0.1683 ms (75 -> 82 % of HBM); seven warps per block at 128 registers measured 0.1829
+    static constexpr int kStages = 6 * kStageBytes <= kRingSmemBudget ? 6 : 4, kMinBlocks = 1, kConsumerWarps = 15;
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : ((m >= 3 && !p.r2_mean) ? 0 : 1); }
     __device__ static void prologue(Shared &) {}
 

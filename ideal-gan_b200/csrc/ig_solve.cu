@@ -1231,7 +1231,10 @@ template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const So
     using I3 = std::integral_constant<int, 3>;
     // up to 8 echoes y (and d^2) stay in registers between the two passes (95 registers at NE = 6, no spills);
     // beyond that y is parked in the thread's own 16 bytes of the stage
-    using W8 = std::integral_constant<int, 8>;
+    // consumer warps per block: 8 for the C2 objective (95 registers, no spills); the uncertainty-aware one spills at 96 registers and runs
+    // 4 % faster on 7 warps + the producer = 8 warps per block = 128 registers per thread (same-call A/B 0.1889 -> 0.1808 ms; C2: 0.1131 -> 0.1194)
+    // (one block of 15 consumer warps on a six-stage ring, which wins for the Rician objective, measured 0.1931 ms masked / 0.2101 unmasked here)
+    using W8 = std::integral_constant<int, UQ ? 7 : 8>;
     if constexpr (NE <= 8) {
         if (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{}, W8{});
         return go(I2{}, I2{}, I1{}, W8{});

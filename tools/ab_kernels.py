@@ -95,12 +95,15 @@ def main():
             if "bwd_ds" in which:
                 rec("a2a_bwd_ds", 24 * ne + 16, lambda: ops.a2a_bwd(acqs, pm, tab, None, up, need_acqs=True))
             del up
-        if "uq" in which or "rician" in which:
+        if "uq" in which or "rician" in which or "pdff" in which:
             pv = torch.rand((nb, 1, H, W, 1), device=dev, generator=g) * 4e-3
             rv = torch.rand((nb, 1, H, W, 1), device=dev, generator=g) * 3e-3
             rm = pm[..., 1:2].contiguous()
             if "uq" in which:
                 rec("a2a_uq_loss", 8 * ne + 40, lambda: ops.a2a_uq_loss(acqs, pm, pv, rm, rv, tab))
+            if "pdff" in which:
+                phm = pm[..., 0:1].contiguous()
+                rec("pdff_unc", 8 * ne + 48, lambda: ops.pdff_unc(acqs, phm, pv, rm, rv, tab))
             if "rician" in which:
                 rec("a2a_rician_loss", 8 * ne + 40, lambda: ops.a2a_rician_loss(acqs, pm, pv, rm, rv, tab))
         if "c4" in which:
