@@ -233,6 +233,21 @@ def main():
     up12 = torch.randn_like(acqs)
     add("ig_a2a_bwd", "ne = 12 acq_to_acq adjoint (dPM only; generic ring, one block per SM, two 100 KB stages)", nb, nv, ne12, 8 * ne12 + 8 + 8 * ne12 + 8,
         lambda: ops.a2a_bwd(acqs, pm, tab, None, up12, need_acqs=False))
+    add("ig_ideal_bwd[wfpm]", "ne = 12 forward-model adjoint (generic ring beyond 8 echoes: RowLossOp<BWD>, one block per SM, three stages)", nb, nv, ne12,
+        8 * ne12 + 24 + 24, lambda: ops.ideal_bwd(L.MODEL_WFPM, maps, tab, ne12, up12))
+    add("ig_ideal_loss[wfpm]", "ne = 12 fused forward objective (generic ring)", nb, nv, ne12, 8 * ne12 + 24 + 24, lambda: ops.ideal_loss(L.MODEL_WFPM, maps, acqs, tab))
+    up_r12 = torch.randn((nb, 2, H, W, 2), device=dev, generator=g)
+    add("ig_get_rho_bwd", "ne = 12 LS solve adjoint (dPM + dS; one voxel per thread beyond 8 echoes)", nb, nv, ne12, 16 * ne12 + 8 + 16 + 8,
+        lambda: ops.get_rho_bwd(acqs, pm, tab, up_r12, None))
+    # an echo count that is not a bucket of the plain kernels: 7 (ring operators are instantiated per echo count)
+    del maps, te, tab, acqs, pm, up12, up_r12
+    torch.cuda.empty_cache()
+    ne7 = 7
+    maps, te, tab, acqs = make(nb, H, W, ne7)
+    pm = (maps[:, 2:3] * 0.95).contiguous()
+    up7 = torch.randn_like(acqs)
+    add("ig_a2a_bwd", "ne = 7 acq_to_acq adjoint (dPM only)", nb, nv, ne7, 16 * ne7 + 16, lambda: ops.a2a_bwd(acqs, pm, tab, None, up7, need_acqs=False))
+    add("ig_a2a_loss", "ne = 7 C2 fused objective (8-echo bucket of the ring kernel)", nb, nv, ne7, 8 * ne7 + 16, lambda: ops.a2a_loss(acqs, pm, tab))
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
 
