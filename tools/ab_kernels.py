@@ -106,6 +106,12 @@ def main():
                 rec("pdff_unc", 8 * ne + 48, lambda: ops.pdff_unc(acqs, phm, pv, rm, rv, tab))
             if "rician" in which:
                 rec("a2a_rician_loss", 8 * ne + 40, lambda: ops.a2a_rician_loss(acqs, pm, pv, rm, rv, tab))
+        if "regs" in which:
+            ls_ = torch.randn((nb, 3, H, W, 1), device=dev, generator=g)
+            dm_ = torch.rand((nb, ne, H, W, 1), device=dev, generator=g)
+            r2_ = torch.rand((nb, 1, H, W, 1), device=dev, generator=g)
+            rec("mag_regs", 2 * (4 * ne + 12 + 4), lambda: ops.mag_regs(ls_, dm_, r2_, (0.1, 0.2, 0.3, 0.4)))
+            del ls_, dm_, r2_
         if "c4" in which:
             mp = torch.rand((nb, 2, H, W, 4), device=dev, generator=g) * 0.5
             mp[:, 1] -= 0.25
