@@ -202,7 +202,7 @@ def test_acq_to_acq_and_config2_loss_vs_reference_vectors(golden, name):
 # (9, 7): odd voxel count -> scalar kernels; (48, 64): whole 512-voxel tiles through tensor-map TMA; (40, 48): 128-voxel
 # rows but a ragged last tile (out-of-range rows of the TMA box); (30, 34): even but not a multiple of 128 -> bulk-copy ring
 @pytest.mark.parametrize("hw", [(9, 7), (48, 64), (40, 48), (30, 34)])
-@pytest.mark.parametrize("ne", [2, 5, 6, 12])
+@pytest.mark.parametrize("ne", [2, 3, 5, 6, 7, 9, 11, 12])      # the ring adjoint has one instantiation per echo count
 def test_acq_to_acq_family_vs_oracle(hw, ne):
     rng = np.random.default_rng(31 + ne)
     H, W = hw

@@ -141,7 +141,7 @@ def _te(nb, ne, rng):
 
 
 @pytest.mark.parametrize("shape", [(3, 16, 16, 6), (2, 40, 48, 5), (1, 384, 384, 6), (2, 64, 96, 8), (2, 64, 64, 3), (2, 40, 48, 9), (1, 192, 192, 12),
-                                   (3, 32, 32, 11)])
+                                   (3, 32, 32, 11), (2, 16, 32, 1), (2, 32, 32, 2), (1, 48, 64, 4), (2, 32, 48, 7), (1, 64, 64, 10)])
 @pytest.mark.parametrize("model,rows", [(L.MODEL_WFPM, 3), (L.MODEL_WFPM, 4), (L.MODEL_FFPD, 3)], ids=["wfpm", "wfpm-bipolar", "ffpd"])
 def test_forward_objective_of_the_complex_row_models_ring_vs_plain_kernel(shape, model, rows):
     """ig_ideal_loss for WF-PM (3 rows, 4 rows with the bipolar one) and ff/pd/phase maps on the generic ring (128-voxel rows, <= 12
