@@ -454,7 +454,9 @@ template <int NE, bool EXACT> struct RicianOp {
     // One block of 15 consumer warps + the producer per SM (16 warps = 4 per scheduler = 128 registers per thread, no spills) on one ring of
     // six stages.  Same-call A/B at 64 x 384 x 384 x 6, masked / unmasked: two blocks of 8 + 1 warps at 96 registers (88 B of spills)
     // 0.2728 / 0.3200 ms, two blocks of 7 + 1 at 128 registers 0.2605 / 0.3014, this 0.2452 / 0.2933.
-    static constexpr int kStages = 6 * kStageBytes + kStatic <= kRingSmemBudget ? 6 : 4, kMinBlocks = 1, kConsumerWarps = 15;
+    static constexpr int kFit = (kRingSmemBudget - kStatic) / kStageBytes;      // 6 stages up to 6 echoes, 4 at 7..9, 3 at 10..12
+    static constexpr int kStages = kFit > 6 ? 6 : kFit, kMinBlocks = 1, kConsumerWarps = 15;
+    static_assert(kStages >= 2, "the ring needs at least two stages in shared memory");
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : ((m >= 3 && !p.r2_mean) ? 0 : 1); }
     __device__ static void prologue(Shared &sh) { stage_bessel_table(sh.btab); }
 
@@ -568,7 +570,7 @@ int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, co
                          const float *tab, int nb, int ne, int nv, float r2_sc, float inv_n, float *g_pm, float *g_phi_var, float *g_r2_mean,
                          float *g_r2_var, float *rho, float *loss, void *scratch, cudaStream_t st) {
     auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
-    if (ne > 8 || nv % 128 != 0 || !aligned16(g_pm) || (rho && !aligned16(rho)) || !al8(g_phi_var) || !al8(g_r2_mean) || !al8(g_r2_var) ||
+    if (ne > 12 || nv % 128 != 0 || !aligned16(g_pm) || (rho && !aligned16(rho)) || !al8(g_phi_var) || !al8(g_r2_mean) || !al8(g_r2_var) ||
         static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24))
         return IG_E_UNSUPPORTED;
     RicianParams p{};
@@ -580,14 +582,7 @@ int a2a_rician_loss_ring(const float *acqs, const float *pm, long pm_bstride, co
     if (!ring_tensor_map(&m.m[1], pm, nv, 2, nb, pm_bstride, 1)) return IG_E_UNSUPPORTED;
     if (!ring_tensor_map(&m.m[2], phi_var, nv, 1, nb, nv, 1)) return IG_E_UNSUPPORTED;
     if (r2_mean && (!ring_tensor_map(&m.m[3], r2_mean, nv, 1, nb, nv, 1) || !ring_tensor_map(&m.m[4], r2_var, nv, 1, nb, nv, 1))) return IG_E_UNSUPPORTED;
-    auto go = [&](auto ne_c) {
-        constexpr int NE = decltype(ne_c)::value;
-        if (ne == NE) return ring_launch<RicianOp<NE, true>>(p, m, st);
-        return ring_launch<RicianOp<NE, false>>(p, m, st);
-    };
-    if (ne <= 4) return go(std::integral_constant<int, 4>{});
-    if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    return go(std::integral_constant<int, 8>{});
+    return dispatch_exact_ne<2, 12>(ne, [&](auto ne_c) { return ring_launch<RicianOp<decltype(ne_c)::value, true>>(p, m, st); });
 }
 
 // =================================================================================================
@@ -615,7 +610,9 @@ template <int NE, bool EXACT> struct PdffUncOp {
     static constexpr int kStageBytes = NE * kRingTileVox * 8 + 4 * kRingTileVox * 4 + ((NE * 64 + 127) / 128) * 128;
     // one block of 15 consumer warps + the producer per SM at 128 registers, one ring of six (four) stages: same-call A/B against two blocks of
     // 8 + 1 warps at 96 registers 0.1842 -> 0.1683 ms (75 -> 82 % of HBM); seven warps per block at 128 registers measured 0.1829
-    static constexpr int kStages = 6 * kStageBytes <= kRingSmemBudget ? 6 : 4, kMinBlocks = 1, kConsumerWarps = 15;
+    static constexpr int kFit = kRingSmemBudget / kStageBytes;
+    static constexpr int kStages = kFit > 6 ? 6 : kFit, kMinBlocks = 1, kConsumerWarps = 15;
+    static_assert(kStages >= 2, "the ring needs at least two stages in shared memory");
     __host__ __device__ static int planes(int m, int ne, const Params &p) { return m == 0 ? ne : ((m >= 3 && !p.r2_mean) ? 0 : 1); }
     __device__ static void prologue(Shared &) {}
 
@@ -716,7 +713,7 @@ template <int NE, bool EXACT> struct PdffUncOp {
 int pdff_unc_ring(const float *acqs, const float *phi_mean, const float *phi_var, const float *r2_mean, const float *r2_var, const float *tab, int nb,
                   int ne, int nv, float r2_sc, float *rho, float *cov, cudaStream_t st) {
     auto al8 = [](const void *q) { return !q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
-    if (ne > 8 || nv % 128 != 0 || !aligned16(rho) || !al8(cov) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24)) return IG_E_UNSUPPORTED;
+    if (ne > 12 || nv % 128 != 0 || !aligned16(rho) || !al8(cov) || static_cast<long>(nb) * (nv / kRingTileVox + 1) >= (1L << 24)) return IG_E_UNSUPPORTED;
     PdffUncRingParams p{};
     p.acqs = acqs; p.phi_mean = phi_mean; p.phi_var = phi_var; p.r2_mean = r2_mean; p.r2_var = r2_var; p.tab = tab; p.rho = rho; p.cov = cov;
     p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
@@ -724,14 +721,7 @@ int pdff_unc_ring(const float *acqs, const float *phi_mean, const float *phi_var
     if (!ring_tensor_map(&m.m[0], acqs, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
     if (!ring_tensor_map(&m.m[1], phi_mean, nv, 1, nb, nv, 1) || !ring_tensor_map(&m.m[2], phi_var, nv, 1, nb, nv, 1)) return IG_E_UNSUPPORTED;
     if (r2_mean && (!ring_tensor_map(&m.m[3], r2_mean, nv, 1, nb, nv, 1) || !ring_tensor_map(&m.m[4], r2_var, nv, 1, nb, nv, 1))) return IG_E_UNSUPPORTED;
-    auto go = [&](auto ne_c) {
-        constexpr int NE = decltype(ne_c)::value;
-        if (ne == NE) return ring_launch<PdffUncOp<NE, true>>(p, m, st);
-        return ring_launch<PdffUncOp<NE, false>>(p, m, st);
-    };
-    if (ne <= 4) return go(std::integral_constant<int, 4>{});
-    if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    return go(std::integral_constant<int, 8>{});
+    return dispatch_exact_ne<2, 12>(ne, [&](auto ne_c) { return ring_launch<PdffUncOp<decltype(ne_c)::value, true>>(p, m, st); });
 }
 
 }  // namespace ig

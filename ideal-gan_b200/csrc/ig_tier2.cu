@@ -725,7 +725,7 @@ extern "C" int ig_pdff_unc(const float *acqs_d, const float *phi_mean_d, const f
     p.acqs = acqs_d; p.phi_mean = phi_mean_d; p.phi_var = phi_var_d; p.r2_mean = r2_mean_d; p.r2_var = r2_var_d; p.tab = tab_d;
     p.rho = rho_d; p.cov = cov_d; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc;
     {
-        // 128-voxel rows, <= 8 echoes: the packed fit on the generic TMA ring (ig_ring_ops.cu, PdffUncOp)
+        // 128-voxel rows, <= 12 echoes: the packed fit on the generic TMA ring (ig_ring_ops.cu, PdffUncOp)
         const int rc = pdff_unc_ring(acqs_d, phi_mean_d, phi_var_d, r2_mean_d, r2_var_d, tab_d, nb, ne, nv, r2_sc, rho_d, cov_d, static_cast<cudaStream_t>(stream));
         if (rc != IG_E_UNSUPPORTED) return rc;
     }

@@ -360,7 +360,7 @@ extern "C" int ig_a2a_rician_loss(const float *acqs_d, const float *pm_d, long p
                           static_cast<const void *>(g_phi_var_d), static_cast<const void *>(g_r2_mean_d), static_cast<const void *>(g_r2_var_d)})
         packed = packed && (!q || (reinterpret_cast<uintptr_t>(q) & 7u) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (packed) {                                    // TMA ring (128-voxel rows, <= 8 echoes): ig_ring_ops.cu
+    if (packed) {                                    // TMA ring (128-voxel rows, <= 12 echoes): ig_ring_ops.cu
         const int rc = a2a_rician_loss_ring(acqs_d, pm_d, pm_bstride, phi_var_d, r2_mean_d, r2_var_d, tab_d, nb, ne, nv, r2_sc, inv_n, g_pm_d,
                                             g_phi_var_d, g_r2_mean_d, g_r2_var_d, rho_d, loss_d, scratch_d, st);
         if (rc != IG_E_UNSUPPORTED) return rc;
