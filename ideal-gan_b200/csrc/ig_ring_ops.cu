@@ -22,18 +22,6 @@ __device__ __forceinline__ cx<pk> conj_rot(pk cw, pk sw, const float4 &r) {
 }
 __device__ __forceinline__ bool all_zero(const float4 &r) { return r.x == 0.f && r.y == 0.f && r.z == 0.f && r.w == 0.f; }
 
-// One instantiation per echo count instead of a bucket with a run-time count: behind `if (e < ne)` the compiler cannot lift the stage reads of
-// the later echoes over the earlier echoes' math, and with 8-16 consumer warps per SM that latency shows (measured, 64 x 384 x 384: the
-// acq_to_acq adjoint at 7 echoes in the 8-echo bucket 0.226 ms against 0.201 ms AT 8 echoes; the WF-PM adjoint at 9 in the 12-echo bucket
-// 0.238 against 0.205 ms at 12).
-template <int N, int HI, typename F> static int dispatch_exact_ne(int ne, F &&f) {
-    if constexpr (N > HI) {
-        return IG_E_UNSUPPORTED;
-    } else {
-        if (ne == N) return f(std::integral_constant<int, N>{});
-        return dispatch_exact_ne<N + 1, HI>(ne, f);
-    }
-}
 
 // =================================================================================================
 // acq_to_acq adjoint (math: ig_solve.cu, a2a_bwd_kernel)

@@ -1214,18 +1214,20 @@ template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const So
         constexpr int S = decltype(st_c)::value, MB = decltype(minb_c)::value, MD = decltype(mode_c)::value;
         constexpr int C = 8, W = decltype(ncw_c)::value;
         using Cfg = TmaCfg<NE, S, C, UQ>;
-        constexpr bool exact_ok = NE <= 8;
+        // one instantiation per echo count up to 12 (the callers dispatch on ne; ring kernels with a run-time count lose the lifting of the later
+        // echoes' stage reads over the earlier echoes' math: profiles/history_r02.md section 11); the 16-echo bucket keeps a run-time count, and
+        // so does the 12-echo instantiation (serves ne = 12 only; its compile-time-count build spills 76 B and measured 0.2380 against 0.2278 ms)
+        constexpr bool kExact = NE <= 11;
         CUtensorMap ma{}, mp{};
         // tensor maps need whole 128-voxel rows; otherwise the tile is fetched plane by plane with bulk copies
         const bool tmap = nv % 128 == 0 && plane_tensor_map(&ma, p.acqs, nv, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, C / 2, ne) &&
                           plane_tensor_map(&mp, p.pm, nv, nb, p.pm_bstride, C / 2, 1);
-        const bool exact = exact_ok && ne == NE;
-        if (tmap) {
-            if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, true, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-            return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, true, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        if (kExact && ne != NE) {
+            set_error("a2a ring: ne=%d dispatched to the %d-echo instantiation", ne, NE);
+            return static_cast<int>(IG_E_NE);
         }
-        if (exact) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, exact_ok, C, MD, W, false, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
-        return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, false, C, MD, W, false, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        if (tmap) return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, kExact, C, MD, W, true, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
+        return launch_tma(p, st, a2a_loss_tma_kernel<NE, MB, S, kExact, C, MD, W, false, UQ, OUT && MD == 1>, Cfg::smem_bytes, Cfg::tile_vox, W * 32 + 32, ma, mp);
     };
     using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
     using I3 = std::integral_constant<int, 3>;
@@ -1236,12 +1238,12 @@ template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const So
     // (one block of 15 consumer warps on a six-stage ring, which wins for the Rician objective, measured 0.1931 ms masked / 0.2101 unmasked here)
     using W8 = std::integral_constant<int, UQ ? 7 : 8>;
     if constexpr (NE <= 8) {
-        if (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{}, W8{});
-        return go(I2{}, I2{}, I1{}, W8{});
+        if constexpr (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{}, W8{});
+        else return go(I2{}, I2{}, I1{}, W8{});
     } else if constexpr (!UQ) {
-        if (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{}, W8{});
-        if (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{}, W8{});
-        return go(I3{}, I1{}, I0{}, W8{});
+        if constexpr (2 * TmaCfg<NE, 3, 8>::smem_bytes <= kBudget) return go(I3{}, I2{}, I0{}, W8{});
+        else if constexpr (2 * TmaCfg<NE, 2, 8>::smem_bytes <= kBudget) return go(I2{}, I2{}, I0{}, W8{});
+        else return go(I3{}, I1{}, I0{}, W8{});
     } else {
         set_error("uncertainty-aware ring kernel: more than 8 echoes");
         return IG_E_UNSUPPORTED;
@@ -1260,11 +1262,7 @@ int a2a_uq_loss_ring(const float *acqs, const float *pm, long pm_bstride, const 
     p.acqs = acqs; p.pm = pm; p.pm_bstride = pm_bstride; p.tab = tab; p.nb = nb; p.ne = ne; p.nv = nv; p.r2_sc = r2_sc; p.inv_n = inv_n;
     p.g_pm = g_pm; p.rho = rho; p.loss = loss; p.scratch = scratch;
     p.phi_var = phi_var; p.r2_mean = r2_mean; p.r2_var = r2_var; p.g_phi_var = g_phi_var; p.g_r2_mean = g_r2_mean; p.g_r2_var = g_r2_var;
-    return dispatch_ne(ne, [&](auto ne_c) {
-        constexpr int NE = decltype(ne_c)::value;
-        if constexpr (NE <= 8) return launch_a2a_ring<NE, true>(p, st);
-        else return static_cast<int>(IG_E_UNSUPPORTED);
-    });
+    return dispatch_exact_ne<2, 8>(ne, [&](auto ne_c) { return launch_a2a_ring<decltype(ne_c)::value, true>(p, st); });
 }
 
 }  // namespace ig
@@ -1382,18 +1380,21 @@ static int a2a_loss_impl(const float *acqs_d, const float *pm_d, long pm_bstride
     const bool packed = nv % 2 == 0 && pm_bstride % 4 == 0 && all_aligned({acqs_d, pm_d, g_pm_d, rho_d, shat_d});
     const bool outputs = rho_d || shat_d;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return dispatch_ne(ne, [&](auto ne_c) {
-        constexpr int NE = decltype(ne_c)::value;
-        // materialised rho_hat / S_hat ride on the ring kernel's register-resident path (NE <= 8); otherwise the plain kernel
-        if (outputs && !(packed && NE <= 8 && ring_tiles(nb, nv) < (1L << 24)))
-            return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
-        // (the ring's work counter is a float atomic, exact up to 2^24 tiles: larger batches take the plain persistent kernel)
-        if (packed && ring_tiles(nb, nv) < (1L << 24)) {
+    // The ring (its work counter is a float atomic, exact up to 2^24 tiles: larger batches take the plain persistent kernel); materialised
+    // rho_hat / S_hat ride on its register-resident path, which holds up to 8 echoes.  One instantiation per echo count up to 12.
+    if (packed && ring_tiles(nb, nv) < (1L << 24) && (!outputs || ne <= 8)) {
+        if (ne > 12) return launch_a2a_ring<16, false>(p, st);
+        return dispatch_exact_ne<2, 12>(ne, [&](auto ne_c) {
+            constexpr int NE = decltype(ne_c)::value;
             if constexpr (NE <= 8) {
                 if (outputs) return launch_a2a_ring<NE, false, true>(p, st);
             }
             return launch_a2a_ring<NE, false>(p, st);
-        }
+        });
+    }
+    return dispatch_ne(ne, [&](auto ne_c) {
+        constexpr int NE = decltype(ne_c)::value;
+        if (outputs) return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, true, 2>, a2a_loss_kernel<NE, float, true, 2>);
         return launch_persistent(packed, p, st, a2a_loss_kernel<NE, pk, false, 2>, a2a_loss_kernel<NE, float, false, 2>);
     });
 }
