@@ -1236,7 +1236,9 @@ template <int NE, bool UQ, bool OUT = false> static int launch_a2a_ring(const So
     // consumer warps per block: 8 for the C2 objective (95 registers, no spills); the uncertainty-aware one spills at 96 registers and runs
     // 4 % faster on 7 warps + the producer = 8 warps per block = 128 registers per thread (same-call A/B 0.1889 -> 0.1808 ms; C2: 0.1131 -> 0.1194)
     // (one block of 15 consumer warps on a six-stage ring, which wins for the Rician objective, measured 0.1931 ms masked / 0.2101 unmasked here)
-    using W8 = std::integral_constant<int, UQ ? 7 : 8>;
+    // the variant that materialises rho_hat / S_hat spills 96-320 B at 96 registers as well: 7 warps measured 0.1951 -> 0.1911 ms at 6 echoes
+    // (95 -> 97 % of HBM; unmasked 92 -> 97 %), 0.2504 -> 0.2420 ms at 8
+    using W8 = std::integral_constant<int, (UQ || OUT) ? 7 : 8>;
     if constexpr (NE <= 8) {
         if constexpr (2 * TmaCfg<NE, 3, 8, UQ>::smem_bytes <= kBudget) return go(I3{}, I2{}, I1{}, W8{});
         else return go(I2{}, I2{}, I1{}, W8{});

@@ -78,6 +78,8 @@ def main():
 
         if "loss" in which:
             rec("a2a_loss", 8 * ne + 16, lambda: ops.a2a_loss(acqs, pm, tab))
+        if "loss_out" in which:
+            rec("a2a_loss_out", 16 * ne + 32, lambda: ops.a2a_loss(acqs, pm, tab, want_rho=True, want_shat=True))
         if "plain" in which:
             # the operators an unmodified train-IDEAL-TEaug.py step reaches (IDEAL_Layer, get_rho and their adjoints, 2..12 echoes) and acq_to_acq forward
             up_r = torch.randn((nb, 2, H, W, 2), device=dev, generator=g)
