@@ -247,7 +247,7 @@ def main():
     pm = (maps[:, 2:3] * 0.95).contiguous()
     up7 = torch.randn_like(acqs)
     add("ig_a2a_bwd", "ne = 7 acq_to_acq adjoint (dPM only)", nb, nv, ne7, 16 * ne7 + 16, lambda: ops.a2a_bwd(acqs, pm, tab, None, up7, need_acqs=False))
-    add("ig_a2a_loss", "ne = 7 C2 fused objective (8-echo bucket of the ring kernel)", nb, nv, ne7, 8 * ne7 + 16, lambda: ops.a2a_loss(acqs, pm, tab))
+    add("ig_a2a_loss", "ne = 7 C2 fused objective (ring kernels are instantiated per echo count)", nb, nv, ne7, 8 * ne7 + 16, lambda: ops.a2a_loss(acqs, pm, tab))
     print(json.dumps({"hbm_peak_gbs": peak, "device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 
 
