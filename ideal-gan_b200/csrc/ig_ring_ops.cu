@@ -259,14 +259,7 @@ int magpha_loss_ring(const float *maps, const float *acqs, const float *tab, int
     RingMaps m{};
     if (!ring_tensor_map(&m.m[0], maps, nv, 4, static_cast<long>(nb) * 2, static_cast<long>(nv) * 4, 2)) return IG_E_UNSUPPORTED;
     if (!ring_tensor_map(&m.m[1], acqs, nv, 2, static_cast<long>(nb) * ne, static_cast<long>(nv) * 2, ne)) return IG_E_UNSUPPORTED;
-    auto go = [&](auto ne_c) {
-        constexpr int NE = decltype(ne_c)::value;
-        if (ne == NE) return ring_launch<MagphaLossOp<NE, true>>(p, m, st);
-        return ring_launch<MagphaLossOp<NE, false>>(p, m, st);
-    };
-    if (ne <= 4) return go(std::integral_constant<int, 4>{});
-    if (ne <= 6) return go(std::integral_constant<int, 6>{});
-    return go(std::integral_constant<int, 8>{});
+    return dispatch_exact_ne<1, 8>(ne, [&](auto ne_c) { return ring_launch<MagphaLossOp<decltype(ne_c)::value, true>>(p, m, st); });
 }
 
 // =================================================================================================

@@ -200,3 +200,30 @@ def test_adjoint_of_the_complex_row_models_ring_vs_plain_kernel_and_oracle(shape
         sig = (orc.IDEAL_mag if model == L.MODEL_FFPD else orc.IDEAL_model)(m, [1.5, torch.from_numpy(te_np)])
         (ref,) = torch.autograd.grad(sig, [m], grad_outputs=gout.cpu())
         assert_close(gmaps.cpu().numpy(), ref.numpy(), 1e-5, "adjoint (ring) vs oracle autograd")
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 48, 3), (2, 40, 48, 5), (1, 64, 64, 7), (2, 32, 32, 8), (1, 16, 32, 1), (1, 192, 192, 6)])
+@pytest.mark.parametrize("ch", [3, 4], ids=["unipolar", "bipolar"])
+def test_mag_phase_objective_ring_vs_plain_kernel(shape, ch):
+    """ig_ideal_loss for the per-species magnitude / phase maps (C4, train-IDEAL-single.py:154-157,175): 4-channel rows on the generic ring, one
+    instantiation per echo count up to 8; measurements that start 8 bytes into an allocation force the plain persistent kernel (3-channel rows
+    always take it)."""
+    nb, H, W, ne = shape
+    rng = np.random.default_rng(41 + nb + ne + ch)
+    maps = torch.from_numpy(synth.magpha_maps(nb, H, W, rng, bipolar=(ch == 4))).cuda()
+    te = torch.from_numpy(_te(nb, ne, rng)).cuda()
+    tab = ops.gen_tables(te, 1.5)
+    sig = ops.ideal_fwd(L.MODEL_MAGPHA, maps, tab, ne)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acqs = torch.where(sig != 0, sig + 0.02 * torch.randn(sig.shape, device="cuda", generator=g), torch.zeros_like(sig)).contiguous()
+    acqs[0, 0, H // 2, W // 2, 1] = 0.0
+    est = (maps * 0.97).contiguous()
+    loss, gmaps, shat = ops.ideal_loss(L.MODEL_MAGPHA, est, acqs, tab, want_shat=True)
+    buf = torch.empty(acqs.numel() + 2, device="cuda")
+    a_off = buf[2:].view_as(acqs)
+    a_off.copy_(acqs)
+    assert a_off.data_ptr() % 16 == 8
+    loss_p, gmaps_p, shat_p = ops.ideal_loss(L.MODEL_MAGPHA, est, a_off, tab, want_shat=True)
+    assert abs(loss.item() - loss_p.item()) <= 2e-6 * abs(loss_p.item())
+    assert_close(gmaps.cpu().numpy(), gmaps_p.cpu().numpy(), 5e-6, "gradient ring vs plain")
+    assert_close(shat.cpu().numpy(), shat_p.cpu().numpy(), 2e-6, "S_hat ring vs plain")
