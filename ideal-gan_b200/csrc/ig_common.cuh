@@ -454,9 +454,7 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 // barrier among the first `count` threads of the block (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void named_barrier(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
-// NE buckets: kernels are instantiated for these echo counts; a call with `ne` echoes runs in the
-// smallest bucket >= ne with the unused echoes predicated off (their table entries are zero).
-// One instantiation per echo count instead of a bucket with a run-time count: behind `if (e < ne)` the compiler cannot lift the stage reads of
+// Ring operators: one instantiation per echo count instead of a bucket with a run-time count: behind `if (e < ne)` the compiler cannot lift the stage reads of
 // the later echoes over the earlier echoes' math, and with 8-16 consumer warps per SM that latency shows (measured, 64 x 384 x 384: the
 // acq_to_acq adjoint at 7 echoes in the 8-echo bucket 0.226 ms against 0.201 ms AT 8 echoes; the WF-PM adjoint at 9 in the 12-echo bucket
 // 0.238 against 0.205 ms at 12).
@@ -469,6 +467,8 @@ template <int N, int HI, typename F> inline int dispatch_exact_ne(int ne, F &&f)
     }
 }
 
+// NE buckets of the plain kernels: they are instantiated for these echo counts; a call with `ne` echoes runs in the
+// smallest bucket >= ne with the unused echoes predicated off (their table entries are zero).
 template <typename F> inline int dispatch_ne(int ne, F &&f) {
     if (ne <= 4) return f(std::integral_constant<int, 4>{});
     if (ne <= 6) return f(std::integral_constant<int, 6>{});

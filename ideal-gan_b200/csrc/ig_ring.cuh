@@ -2,15 +2,16 @@
 // template, so that the other latency-bound operators (acq_to_acq adjoint, the bipolar mag/phase objective, the Rician
 // objective) get the same treatment: loads cost the math warps no registers, no address arithmetic and no scoreboard stalls.
 //
-//   block  = 8 consumer warps + 1 producer warp, persistent (one resident wave)
+//   block  = 8 consumer warps (or Op::kConsumerWarps: 7 or 15) + 1 producer warp, persistent (one resident wave of one or two blocks per SM)
 //   tile   = 512 voxels = 8 chunks of 64 voxels (a consumer warp's unit: two voxels per lane)
 //   stage  = every input plane of one tile + the sample's echo records, delivered by TMA on a "full" mbarrier:
 //            one 3-D tensor-map box {<= 256 floats, rows, planes} per input TENSOR (UTMALDG) + one bulk copy (UBLKCP)
-//   ring   = Op::kStages stages; consumers draw chunks from a shared counter and release a stage through its "empty" mbarrier
+//   ring   = Op::kStages stages; consumers draw chunks from a shared counter and release a stage through its "empty" mbarrier;
+//            the producer ends the ring with one marker stage per eight consumer warps
 //
 // An Op supplies the input tensors (floats per voxel and planes per sample of each), the per-chunk math and its Params; outputs
 // leave straight from registers with streaming stores.  Shapes need whole 128-voxel rows (nv % 128 == 0) and 16-byte aligned
-// bases; everything else stays on the plain kernels.
+// bases; everything else stays on the plain kernels.  Ops are instantiated per echo count (dispatch_exact_ne in ig_common.cuh), not per bucket.
 #pragma once
 #include <cuda.h>
 
